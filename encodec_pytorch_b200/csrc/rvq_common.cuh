@@ -1,0 +1,111 @@
+// Shared definitions for the B200 RVQ library: pack layout, error plumbing, launch counter.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/rvq_b200.h"
+
+namespace rvq {
+
+// ----------------------------------------------------------------------------------------------
+// Pack layout (device memory, caller-allocated, rvq_pack_bytes()):
+//   [0, 256)                 header: 4 x uint64 search counters (+ reserved)
+//   per stage s (stride stage_bytes(K, D), 256-B aligned sections):
+//     tab32   fp32 [K][D]    row-major copy of embed             (gathers, exact re-score)
+//     tab32T  fp32 [D][K]    transposed copy                     (exact SIMT search tiles)
+//     cnorm   fp32 [K]       |c_k|^2
+//     tc      fp16 image     (only D==128 && K%128==0) K/128 chunks of 36864 B, each the
+//                            shared-memory image of a 128-code x 144-K UMMA B operand
+//     meta    StageMeta
+// ----------------------------------------------------------------------------------------------
+constexpr int kHeaderBytes  = 256;
+constexpr int kTcChunkCodes = 128;                 // codes per UMMA N tile
+constexpr int kTcKPad       = 144;                 // 128 dims + 16 augmented K columns
+constexpr int kTcChunkBytes = kTcChunkCodes * kTcKPad * 2;  // 36864
+
+struct StageMeta {
+  float margin_coef;   // delta = margin_coef * (|x| + eps1): two-sided bound on the fp16 score error
+  float xlimit;        // frames with |x| >= xlimit take the exact path (outlier codes / fp16 range)
+  float cref;          // largest norm among non-outlier codes
+  float cmin;          // smallest code norm
+  int   n_outliers;    // codes excluded from the fp16 image (provably non-winning under xlimit)
+  int   reserved[3];
+};
+
+__host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+__host__ __device__ inline bool tc_shape(int K, int D) { return D == 128 && K >= 128 && (K % kTcChunkCodes) == 0; }
+
+struct StageLayout {
+  size_t off_tab32, off_tab32T, off_cnorm, off_tc, off_meta, stride;
+};
+__host__ __device__ inline StageLayout stage_layout(int K, int D) {
+  StageLayout L;
+  size_t o = 0;
+  L.off_tab32 = o;  o += align256(size_t(K) * D * 4);
+  L.off_tab32T = o; o += align256(size_t(K) * D * 4);
+  L.off_cnorm = o;  o += align256(size_t(K) * 4);
+  L.off_tc = o;     o += tc_shape(K, D) ? size_t(K / kTcChunkCodes) * kTcChunkBytes : 0;
+  L.off_meta = o;   o += 256;
+  L.stride = o;
+  return L;
+}
+
+struct PackView {
+  const unsigned char* base;
+  StageLayout L;
+  __host__ __device__ PackView(const void* p, int K, int D) : base((const unsigned char*)p), L(stage_layout(K, D)) {}
+  __host__ __device__ const unsigned char* stage(int s) const { return base + kHeaderBytes + size_t(s) * L.stride; }
+  __host__ __device__ const float* tab32(int s)  const { return (const float*)(stage(s) + L.off_tab32); }
+  __host__ __device__ const float* tab32T(int s) const { return (const float*)(stage(s) + L.off_tab32T); }
+  __host__ __device__ const float* cnorm(int s)  const { return (const float*)(stage(s) + L.off_cnorm); }
+  __host__ __device__ const unsigned char* tc(int s) const { return stage(s) + L.off_tc; }
+  __host__ __device__ const StageMeta* meta(int s) const { return (const StageMeta*)(stage(s) + L.off_meta); }
+  __host__ __device__ unsigned long long* counters() const { return (unsigned long long*)base; }
+};
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);   // records + returns RVQ_ECUDA
+int  check_device();                               // RVQ_OK or RVQ_ENODEV (cached per device)
+void count_launch(int n = 1);
+
+#define RVQ_CUDA(expr)                                             \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return rvq::cuda_fail(_e, #expr);       \
+  } while (0)
+
+#define RVQ_LAUNCH_CHECK(name)                                     \
+  do {                                                             \
+    rvq::count_launch();                                           \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return rvq::cuda_fail(_e, name);        \
+  } while (0)
+
+#define RVQ_REQUIRE(cond, ...)                                     \
+  do {                                                             \
+    if (!(cond)) { rvq::set_error(__VA_ARGS__); return RVQ_EINVAL; } \
+  } while (0)
+
+// frame n = b*T + t  ->  element offset of (b, d=0, t) in a strided [B, D, T] tensor
+struct FrameAddr {
+  int64_t sxb, sxd, sxt; int T;
+  __device__ inline int64_t base(int64_t n) const { int64_t b = n / T; int64_t t = n - b * T; return b * sxb + t * sxt; }
+};
+
+// ---- entry points implemented per translation unit -------------------------------------------
+int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st);
+int simt_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+                int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, double* sqerr,
+                int flags, cudaStream_t st);
+int tc_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+              int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, double* sqerr,
+              int flags, cudaStream_t st);
+
+}  // namespace rvq

@@ -1,0 +1,615 @@
+// fp32 SIMT kernels of the B200 RVQ library: codebook pack, exact (fp32) fused multi-stage
+// search, gather/decode, EMA statistics + update, dead-code replacement, k-means update and the
+// residual-combine backward helper.  The tcgen05 search lives in rvq_tc.cu.
+//
+// Reference behaviour restated here (paths relative to the reference repository):
+//   quantization/core_vq.py:181-189  distance / argmax (ties -> lowest index)
+//   quantization/core_vq.py:357-367  residual encode loop
+//   quantization/core_vq.py:369-375  decode sum order
+//   quantization/core_vq.py:227-235  EMA statistics, Laplace smoothing, table overwrite
+//   quantization/core_vq.py:80-102   k-means
+#include "rvq_common.cuh"
+
+namespace rvq {
+
+// ================================================================================================
+// pack
+// ================================================================================================
+struct PtrTable32 { const float* p[32]; };
+struct MutPtrTable32 { float* p[32]; };
+
+// copy embed -> tab32 and tab32T through a 32x32 shared tile (coalesced both ways)
+__global__ void pack_copy_kernel(PtrTable32 src, unsigned char* pack, int stage_base, int K, int D) {
+  __shared__ float tile[32][33];
+  const int s = blockIdx.z;
+  PackView pv(pack, K, D);
+  const float* in = src.p[s];
+  float* t32 = const_cast<float*>(pv.tab32(stage_base + s));
+  float* t32T = const_cast<float*>(pv.tab32T(stage_base + s));
+  const int k0 = blockIdx.y * 32, d0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int k = k0 + i, d = d0 + threadIdx.x;
+    float v = 0.f;
+    if (k < K && d < D) { v = in[size_t(k) * D + d]; t32[size_t(k) * D + d] = v; }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int d = d0 + i, k = k0 + threadIdx.x;
+    if (k < K && d < D) t32T[size_t(d) * K + k] = tile[threadIdx.x][i];
+  }
+}
+
+// one block per stage: |c|^2, norm statistics, margin metadata and the fp16 UMMA image
+constexpr float kBetaFp16   = 4.1f * 4.8828125e-4f;  // 4.1 * 2^-11: |score error| <= beta*|x|*|c| (fp16 operands)
+constexpr float kEps1       = 1e-3f;                 // absolute slack for fp16 subnormals
+constexpr float kOutlierMul = 64.f;                  // codes with |c| > 64 * median are outliers
+constexpr float kBigScore   = 60000.f;               // fp16-representable score of an outlier code
+constexpr float kHalfSafe   = 3.0e4f;                // |2c| elements and |c|^2 must stay below fp16 max
+
+__global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, int stage_base, int K, int D) {
+  extern __shared__ float sh[];          // [Kpow2] sorted norms, then [K] flags
+  const int s = stage_base + blockIdx.x;
+  PackView pv(pack, K, D);
+  const float* t32 = pv.tab32(s);
+  float* cn = const_cast<float*>(pv.cnorm(s));
+  const bool tc = tc_shape(K, D);
+  int Kp = 1; while (Kp < K) Kp <<= 1;
+  float* norms = sh;                      // Kp
+  unsigned char* outl = (unsigned char*)(sh + Kp);   // K
+
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float nv = __int_as_float(0x7f800000);
+    if (k < K) {
+      const float* row = t32 + size_t(k) * D;
+      float acc = 0.f, amax = 0.f;
+      for (int d = 0; d < D; ++d) { float v = row[d]; acc = fmaf(v, v, acc); amax = fmaxf(amax, fabsf(v)); }
+      cn[k] = acc;
+      nv = sqrtf(acc);
+      // range flags for the fp16 image: B holds -2c, the augmented column holds |c|^2
+      outl[k] = (!(2.f * amax < kHalfSafe) || !(acc < kHalfSafe)) ? 1 : 0;
+    }
+    norms[k] = nv;
+  }
+  __syncthreads();
+  if (!tc) return;
+
+  // bitonic sort of the norms (ascending); +inf padding sinks to the end
+  for (int size = 2; size <= Kp; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+        int j = i ^ stride;
+        if (j > i) {
+          bool up = ((i & size) == 0);
+          float a = norms[i], b = norms[j];
+          if ((a > b) == up) { norms[i] = b; norms[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __shared__ float s_thr, s_cref, s_cmin, s_outmin;
+  __shared__ int s_nout;
+  if (threadIdx.x == 0) {
+    float med = norms[K / 2];
+    s_thr = kOutlierMul * med;
+    s_cmin = norms[0];
+    s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0;
+  }
+  __syncthreads();
+  // classify (a code is an outlier by norm ratio or by fp16 range); reduce cref / min outlier norm
+  {
+    float lcref = 0.f, loutmin = __int_as_float(0x7f800000); int lnout = 0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float nv = sqrtf(cn[k]);
+      bool o = outl[k] || !(nv <= s_thr);
+      outl[k] = o ? 1 : 0;
+      if (o) { loutmin = fminf(loutmin, nv); ++lnout; } else lcref = fmaxf(lcref, nv);
+    }
+    atomicMax((int*)&s_cref, __float_as_int(lcref));          // non-negative floats order as ints
+    atomicMin((int*)&s_outmin, __float_as_int(loutmin));
+    atomicAdd(&s_nout, lnout);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    StageMeta m;
+    m.cref = s_cref; m.cmin = s_cmin; m.n_outliers = s_nout;
+    m.reserved[0] = m.reserved[1] = m.reserved[2] = 0;
+    m.margin_coef = 2.f * kBetaFp16 * (s_cref + kEps1);
+    // |x| bound under which (a) outlier codes provably lose to the smallest-norm code and
+    // (b) every live score + margin stays below the outlier score, (c) x fits fp16.
+    float xl = 6.0e4f;
+    if (s_nout > 0) {
+      xl = fminf(xl, 0.5f * (s_outmin - s_cmin));
+      float denom = 2.f * s_cmin + m.margin_coef + 1e-30f;
+      xl = fminf(xl, (0.9f * kBigScore - s_cmin * s_cmin) / denom);
+    }
+    if (s_nout >= K) xl = 0.f;
+    m.xlimit = xl > 0.f ? xl : 0.f;
+    *const_cast<StageMeta*>(pv.meta(s)) = m;
+  }
+  // fp16 image: chunk c (128 codes) = 18 K-groups of 8 halves; element (row r, group g) at
+  //   c*36864 + g*2048 + r*16   (K-major, no swizzle: core matrix = 8 rows x 16 B contiguous)
+  unsigned char* img = const_cast<unsigned char*>(pv.tc(s));
+  const int ngroups = kTcKPad / 8;   // 18
+  for (int i = threadIdx.x; i < K * ngroups; i += blockDim.x) {
+    int g = i / K, k = i - g * K;     // consecutive threads -> consecutive codes -> contiguous 16 B
+    int c = k / kTcChunkCodes, r = k % kTcChunkCodes;
+    bool o = outl[k] != 0;
+    __align__(16) __half h[8];
+    if (g < 16) {
+      const float* row = t32 + size_t(k) * D + g * 8;
+      #pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(o ? 0.f : -2.f * row[j]);
+    } else if (g == 16) {
+      float ee = o ? kBigScore : cn[k];
+      __half hi = __float2half_rn(ee);
+      __half lo = __float2half_rn(o ? 0.f : ee - __half2float(hi));
+      h[0] = hi; h[1] = lo;
+      #pragma unroll
+      for (int j = 2; j < 8; ++j) h[j] = __float2half_rn(0.f);
+    } else {
+      #pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(0.f);
+    }
+    *reinterpret_cast<uint4*>(img + size_t(c) * kTcChunkBytes + size_t(g) * 2048 + size_t(r) * 16) =
+        *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st) {
+  int Kp = 1; while (Kp < K) Kp <<= 1;
+  size_t meta_smem = size_t(Kp) * 4 + size_t(K);
+  RVQ_REQUIRE(meta_smem <= 200 * 1024, "rvq_pack: codebook_size %d too large", K);
+  RVQ_CUDA(cudaFuncSetAttribute(pack_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta_smem));
+  RVQ_CUDA(cudaMemsetAsync(pack, 0, kHeaderBytes, st));
+  for (int s0 = 0; s0 < n_q; s0 += 32) {
+    int ns = n_q - s0 < 32 ? n_q - s0 : 32;
+    PtrTable32 tab;
+    for (int i = 0; i < 32; ++i) tab.p[i] = i < ns ? embed_ptrs_host[s0 + i] : nullptr;
+    dim3 grid((D + 31) / 32, (K + 31) / 32, ns), block(32, 8);
+    pack_copy_kernel<<<grid, block, 0, st>>>(tab, (unsigned char*)pack, s0, K, D);
+    RVQ_LAUNCH_CHECK("pack_copy_kernel");
+    pack_meta_kernel<<<ns, 1024, meta_smem, st>>>((unsigned char*)pack, s0, K, D);
+    RVQ_LAUNCH_CHECK("pack_meta_kernel");
+  }
+  return RVQ_OK;
+}
+
+// ================================================================================================
+// exact fused multi-stage search (fp32 SIMT).  Block = 256 threads, tile = 64 frames.
+// ================================================================================================
+constexpr int kXF = 64;    // frames per block
+constexpr int kXC = 64;    // codes per chunk
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(256, 2)
+exact_encode_kernel(const unsigned char* pack, int K, int D,
+                    const float* __restrict__ x, FrameAddr fa, int64_t N,
+                    int stage0, int n_q, int64_t* __restrict__ codes,
+                    float* __restrict__ quantized, double* __restrict__ sqerr, int ste) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                    // [D][64] residual, frame-contiguous
+  float* cs = xs + size_t(D) * kXF;    // [D][64] codebook chunk, code-contiguous
+  float* xx = cs + size_t(D) * kXC;    // [64]
+  float* xpart = xx + kXF;             // [4][64]
+  int*   win = (int*)(xpart + 4 * kXF);// [64]
+  float* red = (float*)(win + kXF);    // [8]
+  float* qs = red + 8;                 // [D][64] running quantized sum (only when requested)
+
+  PackView pv(pack, K, D);
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t n0 = int64_t(blockIdx.x) * kXF;
+  const int uf = tid & 63, uq = tid >> 6;          // update-phase mapping: frame, dim quarter
+  const int dq = D >> 2;                            // dims per quarter (D % 4 == 0)
+  const int64_t un = n0 + uf;
+  const bool uvalid = un < N;
+
+  // load the latent tile (coalesced along t when sxt == 1)
+  {
+    const int64_t xb = uvalid ? fa.base(un) : 0;
+    float part = 0.f;
+    for (int d = uq * dq; d < (uq + 1) * dq; ++d) {
+      float v = uvalid ? x[xb + int64_t(d) * fa.sxd] : 0.f;
+      xs[d * kXF + uf] = v;
+      part = fmaf(v, v, part);
+    }
+    xpart[uq * kXF + uf] = part;
+  }
+  if (quantized != nullptr)
+    for (int d = uq * dq; d < (uq + 1) * dq; ++d) qs[d * kXF + uf] = 0.f;
+  __syncthreads();
+  if (tid < kXF) xx[tid] = ((xpart[tid] + xpart[kXF + tid]) + xpart[2 * kXF + tid]) + xpart[3 * kXF + tid];
+
+  for (int si = 0; si < n_q; ++si) {
+    const int s = stage0 + si;
+    const float* t32T = pv.tab32T(s);
+    const float* t32 = pv.tab32(s);
+    const float* cn = pv.cnorm(s);
+    float bd[4]; int bi[4];
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) { bd[i] = __int_as_float(0x7f800000); bi[i] = 0x7fffffff; }
+
+    for (int c0 = 0; c0 < K; c0 += kXC) {
+      __syncthreads();   // previous chunk consumed / residual + xx updated
+      for (int i = tid; i < D * (kXC / 4); i += 256) {
+        int d = i / (kXC / 4), j4 = (i - d * (kXC / 4)) * 4;
+        float4 v;
+        const float* src = t32T + size_t(d) * K + c0 + j4;
+        if (c0 + j4 + 3 < K && ((K & 3) == 0)) v = *reinterpret_cast<const float4*>(src);
+        else {
+          v.x = c0 + j4 + 0 < K ? src[0] : 0.f; v.y = c0 + j4 + 1 < K ? src[1] : 0.f;
+          v.z = c0 + j4 + 2 < K ? src[2] : 0.f; v.w = c0 + j4 + 3 < K ? src[3] : 0.f;
+        }
+        *reinterpret_cast<float4*>(cs + d * kXC + j4) = v;
+      }
+      __syncthreads();
+      float acc[4][4];
+      #pragma unroll
+      for (int i = 0; i < 4; ++i)
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      #pragma unroll 4
+      for (int d = 0; d < D; ++d) {
+        float4 xv = *reinterpret_cast<const float4*>(xs + d * kXF + ty * 4);
+        float4 cv = *reinterpret_cast<const float4*>(cs + d * kXC + tx * 4);
+        float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+          #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (DIRECT) { float t = xa[i] - ca[j]; acc[i][j] = fmaf(t, t, acc[i][j]); }
+            else acc[i][j] = fmaf(xa[i], ca[j], acc[i][j]);
+          }
+      }
+      #pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int code = c0 + tx * 4 + j;
+        if (code < K) {
+          float cnj = DIRECT ? 0.f : cn[code];
+          #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // core_vq.py:183-187: (|x|^2 - 2 x.e) + |e|^2, maximised after negation
+            float dist = DIRECT ? acc[i][j] : (xx[ty * 4 + i] - 2.f * acc[i][j]) + cnj;
+            if (dist < bd[i]) { bd[i] = dist; bi[i] = code; }
+          }
+        }
+      }
+    }
+    // reduce over the 16 code lanes of each frame row; ties -> lowest index
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      #pragma unroll
+      for (int off = 8; off > 0; off >>= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, bd[i], off);
+        int oi = __shfl_xor_sync(0xffffffffu, bi[i], off);
+        if (od < bd[i] || (od == bd[i] && oi < bi[i])) { bd[i] = od; bi[i] = oi; }
+      }
+      // NaN rows never satisfy '<': fall back to code 0 like an all-NaN argmax
+      if (tx == 0) win[ty * 4 + i] = bi[i] == 0x7fffffff ? 0 : bi[i];
+    }
+    __syncthreads();
+    // gather + residual update (+ straight-through arithmetic), exact fp32
+    {
+      const int idx = win[uf];
+      const float* row = t32 + size_t(idx) * D;
+      float part = 0.f;
+      for (int d = uq * dq; d < (uq + 1) * dq; ++d) {
+        float r = xs[d * kXF + uf];
+        float q = row[d];
+        if (ste) q = r + (q - r);
+        float rn = r - q;
+        xs[d * kXF + uf] = rn;
+        part = fmaf(rn, rn, part);
+        if (quantized != nullptr) qs[d * kXF + uf] += q;
+      }
+      xpart[uq * kXF + uf] = part;
+      if (uvalid && uq == 0) codes[int64_t(si) * N + un] = idx;
+      if (sqerr != nullptr) {
+        float v = uvalid ? part : 0.f;
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < kXF) xx[tid] = ((xpart[tid] + xpart[kXF + tid]) + xpart[2 * kXF + tid]) + xpart[3 * kXF + tid];
+    if (sqerr != nullptr && tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += (double)red[i];
+      atomicAdd(&sqerr[si], t);
+    }
+  }
+  if (quantized != nullptr) {
+    __syncthreads();
+    // frame-major store: consecutive threads write consecutive dims of one frame
+    for (int i = tid; i < kXF * D; i += 256) {
+      int f = i / D, d = i - f * D;
+      if (n0 + f < N) quantized[(n0 + f) * D + d] = qs[d * kXF + f];
+    }
+  }
+}
+
+int simt_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+                int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, double* sqerr,
+                int flags, cudaStream_t st) {
+  RVQ_REQUIRE(D % 4 == 0 && D >= 4 && D <= 256, "rvq_encode: dimension %d unsupported (multiple of 4, <= 256)", D);
+  RVQ_REQUIRE(K >= 1, "rvq_encode: codebook_size %d", K);
+  const int64_t N = int64_t(B) * T;
+  if (N == 0 || n_q == 0) return RVQ_OK;
+  size_t smem = (size_t(D) * (kXF + kXC + (quantized ? kXF : 0)) + kXF + 4 * kXF + kXF + 8) * 4;
+  FrameAddr fa{sxb, sxd, sxt, T};
+  unsigned grid = unsigned((N + kXF - 1) / kXF);
+  const bool direct = (flags & RVQ_FLAG_DIRECT_DIST) != 0;
+  auto kern = direct ? exact_encode_kernel<true> : exact_encode_kernel<false>;
+  RVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, 256, smem, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0, n_q, codes, quantized,
+                                sqerr, (flags & RVQ_FLAG_STE) ? 1 : 0);
+  RVQ_LAUNCH_CHECK("exact_encode_kernel");
+  return RVQ_OK;
+}
+
+// ================================================================================================
+// chain kernels: one warp per frame walks the stages (decode / EMA statistics / residual combine)
+// ================================================================================================
+enum ChainMode { kDecode = 0, kStats = 1, kCombine = 2 };
+
+__device__ __forceinline__ void red_add_f4(float* addr, float4 v) {
+#if __CUDA_ARCH__ >= 900
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+  atomicAdd(addr, v.x); atomicAdd(addr + 1, v.y); atomicAdd(addr + 2, v.z); atomicAdd(addr + 3, v.w);
+#endif
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+chain_kernel(const unsigned char* pack, int K, int D,
+             const float* __restrict__ x, FrameAddr fa, int64_t N, int stage0, int n_q,
+             const int64_t* __restrict__ codes, int64_t scq, int64_t scb, int64_t sct, int T,
+             const float* __restrict__ w, float* __restrict__ out,
+             float* __restrict__ counts, float* __restrict__ embed_sum, int ste) {
+  PackView pv(pack, K, D);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int nd4 = D >> 2;     // float4 groups per frame (D % 4 == 0)
+  for (int64_t n = warp; n < N; n += nwarps) {
+    const int64_t b = n / T, t = n - b * T;
+    for (int g0 = 0; g0 < nd4; g0 += 32) {
+      const int g = g0 + lane;
+      const bool act = g < nd4;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f), acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE != kDecode && act) {
+        const int64_t xb = fa.base(n) + int64_t(g) * 4 * fa.sxd;
+        r.x = x[xb]; r.y = x[xb + fa.sxd]; r.z = x[xb + 2 * fa.sxd]; r.w = x[xb + 3 * fa.sxd];
+      }
+      for (int s0 = 0; s0 < n_q; s0 += 32) {
+        // lane i fetches the code of stage s0+i once; broadcast per stage below
+        int mycode = 0;
+        if (s0 + lane < n_q) {
+          int64_t c = codes[int64_t(s0 + lane) * scq + b * scb + t * sct];
+          mycode = c < 0 ? 0 : (c >= K ? K - 1 : int(c));
+        }
+        const int ns = n_q - s0 < 32 ? n_q - s0 : 32;
+        for (int i = 0; i < ns; ++i) {
+          const int s = stage0 + s0 + i;
+          const int idx = __shfl_sync(0xffffffffu, mycode, i);
+          if (MODE == kStats && g0 == 0 && lane == 0) atomicAdd(&counts[size_t(s0 + i) * K + idx], 1.0f);
+          if (!act) continue;
+          float4 q = *reinterpret_cast<const float4*>(pv.tab32(s) + size_t(idx) * D + g * 4);
+          if (MODE == kDecode) {
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+          } else {
+            if (MODE == kStats) red_add_f4(embed_sum + (size_t(s0 + i) * K + idx) * D + g * 4, r);
+            if (ste) { q.x = r.x + (q.x - r.x); q.y = r.y + (q.y - r.y); q.z = r.z + (q.z - r.z); q.w = r.w + (q.w - r.w); }
+            r.x -= q.x; r.y -= q.y; r.z -= q.z; r.w -= q.w;
+            if (MODE == kCombine) {
+              const float ws = w[s0 + i];
+              acc.x = fmaf(ws, r.x, acc.x); acc.y = fmaf(ws, r.y, acc.y);
+              acc.z = fmaf(ws, r.z, acc.z); acc.w = fmaf(ws, r.w, acc.w);
+            }
+          }
+        }
+      }
+      if (MODE != kStats && act) *reinterpret_cast<float4*>(out + n * D + g * 4) = acc;
+    }
+  }
+}
+
+static unsigned chain_grid(int64_t N) {
+  int64_t blocks = (N + 7) / 8;              // 8 warps per block, one frame per warp per pass
+  const int64_t cap = 148 * 16;              // persistent-ish: a few waves over 148 SMs
+  if (blocks > cap) blocks = cap;
+  return unsigned(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace rvq
+
+using namespace rvq;
+
+// ------------------------------------------------------------------------------------------------
+// EMA apply / expiry / k-means update kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ema_apply_kernel(MutPtrTable32 cs_tab, MutPtrTable32 ea_tab, MutPtrTable32 em_tab, int stage_base, int K, int D,
+                 const float* __restrict__ counts, const float* __restrict__ embed_sum,
+                 float decay, float alpha, float eps, float keps) {
+  __shared__ float red[32];
+  __shared__ float s_total;
+  const int s = blockIdx.x;
+  float* cs = cs_tab.p[s];
+  float* ea = ea_tab.p[s];
+  float* em = em_tab.p[s];
+  const float* cnt = counts + size_t(stage_base + s) * K;
+  const float* es = embed_sum + size_t(stage_base + s) * K * D;
+  // cluster_size <- decay*cluster_size + (1-decay)*bincount   (core_vq.py:227, :49-56)
+  float part = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float v = cs[k] * decay + alpha * cnt[k];
+    cs[k] = v;
+    part += v;
+  }
+  #pragma unroll
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) s_total = v;
+  }
+  __syncthreads();
+  const float total = s_total;
+  // embed_avg <- EMA; embed <- embed_avg / (laplace(cluster_size) * total)   (core_vq.py:229-235)
+  const int n = K * D;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int k = i / D;
+    float a = ea[i] * decay + alpha * es[i];
+    ea[i] = a;
+    float sm = (cs[k] + eps) / (total + keps) * total;
+    em[i] = a / sm;
+  }
+}
+
+__global__ void expire_replace_kernel(float* embed, const float* __restrict__ cluster_size,
+                                      const float* __restrict__ samples, int K, int D, float thr) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * D && cluster_size[i / D] < thr) embed[i] = samples[i];
+}
+
+__global__ void kmeans_scatter_kernel(const float* __restrict__ samples, int64_t N, int D,
+                                      const int64_t* __restrict__ buckets, int K,
+                                      float* sums, unsigned long long* bins) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t n = warp; n < N; n += nwarps) {
+    int64_t k = buckets[n];
+    if (k < 0 || k >= K) continue;
+    if (lane == 0) atomicAdd(&bins[k], 1ull);
+    for (int d = lane; d < D; d += 32) atomicAdd(&sums[k * D + d], samples[n * D + d]);
+  }
+}
+
+__global__ void kmeans_finalize_kernel(float* means, const float* __restrict__ sums,
+                                       const unsigned long long* __restrict__ bins, int K, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * D) {
+    unsigned long long b = bins[i / D];
+    if (b != 0) means[i] = sums[i] / float((long long)b);   // empty clusters keep the old mean (:100)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI entry points served by this translation unit
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int rvq_decode(const void* pack, int K, int D, const int64_t* codes, int64_t scq, int64_t scb, int64_t sct,
+               int n_q, int B, int T, float* out, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(pack && out && (codes || n_q == 0), "rvq_decode: null pointer");
+  RVQ_REQUIRE(D % 4 == 0 && D > 0 && K > 0 && n_q >= 0 && B >= 0 && T >= 0, "rvq_decode: bad shape K=%d D=%d n_q=%d", K, D, n_q);
+  const int64_t N = int64_t(B) * T;
+  if (N == 0) return RVQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FrameAddr fa{0, 0, 0, T};
+  chain_kernel<kDecode><<<chain_grid(N), 256, 0, st>>>((const unsigned char*)pack, K, D, nullptr, fa, N, 0, n_q,
+                                                      codes, scq, scb, sct, T, nullptr, out, nullptr, nullptr, 0);
+  RVQ_LAUNCH_CHECK("chain_kernel<decode>");
+  return RVQ_OK;
+}
+
+int rvq_ema_stats(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+                  int B, int T, int stage0, int n_q, const int64_t* codes, float* counts, float* embed_sum,
+                  int flags, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(pack && counts && embed_sum, "rvq_ema_stats: null pointer");
+  RVQ_REQUIRE(D % 4 == 0 && D > 0 && K > 0 && n_q >= 0, "rvq_ema_stats: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  RVQ_CUDA(cudaMemsetAsync(counts, 0, size_t(n_q) * K * 4, st));
+  RVQ_CUDA(cudaMemsetAsync(embed_sum, 0, size_t(n_q) * K * D * 4, st));
+  const int64_t N = int64_t(B) * T;
+  if (N == 0 || n_q == 0) return RVQ_OK;
+  RVQ_REQUIRE(x && codes, "rvq_ema_stats: null pointer");
+  FrameAddr fa{sxb, sxd, sxt, T};
+  chain_kernel<kStats><<<chain_grid(N), 256, 0, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0, n_q, codes,
+                                                     int64_t(B) * T, T, 1, T, nullptr, nullptr, counts, embed_sum,
+                                                     (flags & RVQ_FLAG_STE) ? 1 : 0);
+  RVQ_LAUNCH_CHECK("chain_kernel<stats>");
+  return RVQ_OK;
+}
+
+int rvq_residual_combine(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+                         int B, int T, int stage0, int n_q, const int64_t* codes, const float* w, float* out,
+                         int flags, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(pack && out, "rvq_residual_combine: null pointer");
+  RVQ_REQUIRE(D % 4 == 0 && D > 0 && K > 0 && n_q >= 0, "rvq_residual_combine: bad shape");
+  const int64_t N = int64_t(B) * T;
+  if (N == 0) return RVQ_OK;
+  RVQ_REQUIRE(x && (n_q == 0 || (codes && w)), "rvq_residual_combine: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  FrameAddr fa{sxb, sxd, sxt, T};
+  chain_kernel<kCombine><<<chain_grid(N), 256, 0, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0, n_q, codes,
+                                                       int64_t(B) * T, T, 1, T, w, out, nullptr, nullptr,
+                                                       (flags & RVQ_FLAG_STE) ? 1 : 0);
+  RVQ_LAUNCH_CHECK("chain_kernel<combine>");
+  return RVQ_OK;
+}
+
+int rvq_ema_apply(float* const* cluster_size_ptrs_host, float* const* embed_avg_ptrs_host,
+                  float* const* embed_ptrs_host, int n_q, int K, int D, const float* counts,
+                  const float* embed_sum, double decay, double epsilon, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(cluster_size_ptrs_host && embed_avg_ptrs_host && embed_ptrs_host && counts && embed_sum,
+              "rvq_ema_apply: null pointer");
+  RVQ_REQUIRE(K > 0 && D > 0 && n_q >= 0, "rvq_ema_apply: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float alpha = float(1.0 - decay);             // python: (1 - decay) in double, then fp32
+  const float keps = float(double(K) * epsilon);
+  for (int s0 = 0; s0 < n_q; s0 += 32) {
+    int ns = n_q - s0 < 32 ? n_q - s0 : 32;
+    MutPtrTable32 a, b, c;
+    for (int i = 0; i < 32; ++i) {
+      a.p[i] = i < ns ? cluster_size_ptrs_host[s0 + i] : nullptr;
+      b.p[i] = i < ns ? embed_avg_ptrs_host[s0 + i] : nullptr;
+      c.p[i] = i < ns ? embed_ptrs_host[s0 + i] : nullptr;
+    }
+    ema_apply_kernel<<<ns, 1024, 0, st>>>(a, b, c, s0, K, D, counts, embed_sum, float(decay), alpha, float(epsilon), keps);
+    RVQ_LAUNCH_CHECK("ema_apply_kernel");
+  }
+  return RVQ_OK;
+}
+
+int rvq_expire_replace(float* embed, const float* cluster_size, const float* samples, int K, int D,
+                       float threshold, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(embed && cluster_size && samples && K > 0 && D > 0, "rvq_expire_replace: bad argument");
+  int n = K * D;
+  expire_replace_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(embed, cluster_size, samples, K, D, threshold);
+  RVQ_LAUNCH_CHECK("expire_replace_kernel");
+  return RVQ_OK;
+}
+
+int rvq_kmeans_update(const float* samples, int64_t N, int D, const int64_t* buckets, int K, float* means,
+                      int64_t* bins, float* sums, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(samples && buckets && means && bins && sums && K > 0 && D > 0 && N >= 0, "rvq_kmeans_update: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  RVQ_CUDA(cudaMemsetAsync(bins, 0, size_t(K) * 8, st));
+  RVQ_CUDA(cudaMemsetAsync(sums, 0, size_t(K) * D * 4, st));
+  if (N > 0) {
+    kmeans_scatter_kernel<<<chain_grid(N), 256, 0, st>>>(samples, N, D, buckets, K, sums, (unsigned long long*)bins);
+    RVQ_LAUNCH_CHECK("kmeans_scatter_kernel");
+  }
+  int n = K * D;
+  kmeans_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(means, sums, (const unsigned long long*)bins, K, D);
+  RVQ_LAUNCH_CHECK("kmeans_finalize_kernel");
+  return RVQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+/*
+ * rvq_b200.h -- C ABI of the B200-native EnCodec residual vector quantizer.
+ *
+ * Drop-in boundary for the hot path of Madhudorai/encodec-pytorch
+ * (quantization/core_vq.py + quantization/vq.py).  The Python host mirror in
+ * encodec_pytorch_b200/quantization/ binds these with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer
+ *     unless its name ends in _host;
+ *   - the library never allocates or frees caller-visible memory: outputs and
+ *     scratch are caller-allocated (the host mirror uses torch tensors);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     every call is asynchronous on that stream and does no host sync;
+ *   - return 0 on success, a negative RVQ_E* code on failure; the message is
+ *     available from rvq_last_error() (thread-local);
+ *   - frames are the B*T latent vectors of a [B, D, T] tensor, flattened
+ *     b-major / t-minor exactly like core_vq.py:290 + :178;
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every
+ *     compute entry point fails with RVQ_ENODEV.
+ */
+#ifndef RVQ_B200_H
+#define RVQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVQ_ABI_VERSION 1
+
+#define RVQ_OK        0
+#define RVQ_EINVAL   -1   /* bad argument / unsupported shape              */
+#define RVQ_ENODEV   -2   /* no sm_100 CUDA device                         */
+#define RVQ_ECUDA    -3   /* CUDA runtime error (message has the detail)   */
+#define RVQ_ESIZE    -4   /* caller buffer too small                       */
+
+/* rvq_encode / rvq_ema_stats / rvq_residual_combine flags */
+#define RVQ_FLAG_STE          1  /* training arithmetic of core_vq.py:309/:348: q <- r + (q - r) */
+#define RVQ_FLAG_FORCE_EXACT  2  /* use the fp32 SIMT search even where the tcgen05 path applies   */
+#define RVQ_FLAG_DIRECT_DIST  4  /* k-means distance sum((x-c)^2) of core_vq.py:86-91 (exact path)  */
+
+int         rvq_version(void);                 /* RVQ_ABI_VERSION                                    */
+const char* rvq_last_error(void);              /* last error message of the calling thread           */
+int         rvq_device_ok(void);               /* 0 if the current device is sm_100, else RVQ_ENODEV */
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+uint64_t    rvq_launch_count(void);
+
+/* ---- codebook pack ---------------------------------------------------------------------------
+ * The search image of n_q codebooks [K, D] fp32 (EuclideanCodebook.embed, core_vq.py:143):
+ * fp32 copy [n_q,K,D], transposed fp32 copy [n_q,D,K], |c|^2 [n_q,K], and (D==128, K%128==0)
+ * the fp16 UMMA operand image + per-stage margin metadata used by the tcgen05 search.
+ * embed_ptrs_host: HOST array of n_q DEVICE pointers (the per-stage `embed` buffers).          */
+size_t rvq_pack_bytes(int n_q, int K, int D);
+int    rvq_pack(const float* const* embed_ptrs_host, int n_q, int K, int D,
+                void* pack, size_t pack_bytes, void* stream);
+
+/* ---- encode: replaces ResidualVectorQuantization.encode (core_vq.py:357-367) and the search /
+ * gather / residual part of .forward (core_vq.py:337-355 with :212-221, :301-324).
+ *   x            fp32 [B, D, T] with ELEMENT strides (sxb, sxd, sxt)
+ *   stage0,n_q   stages [stage0, stage0+n_q) of the pack are applied in order
+ *   codes        int64 [n_q, B, T] contiguous (out)
+ *   quantized    fp32 [B, T, D] contiguous (out) or NULL: sum over stages, in stage order, of the
+ *                gathered codewords (of the straight-through values with RVQ_FLAG_STE)
+ *   stage_sqerr  double [n_q] (out, accumulated by atomics; caller zeroes) or NULL:
+ *                sum over frames and dims of (q_i - r_i)^2 -> commitment loss numerator (:319)   */
+int rvq_encode(const void* pack, int K, int D,
+               const float* x, int64_t sxb, int64_t sxd, int64_t sxt, int B, int T,
+               int stage0, int n_q,
+               int64_t* codes, float* quantized, double* stage_sqerr,
+               int flags, void* stream);
+
+/* ---- decode: replaces ResidualVectorQuantization.decode (core_vq.py:369-375).
+ *   codes  int64 [n_q, B, T] with ELEMENT strides (scq, scb, sct) (model.py:188 passes a transposed view)
+ *   out    fp32 [B, T, D] contiguous: ((0 + e_0[c_0]) + e_1[c_1]) + ...                          */
+int rvq_decode(const void* pack, int K, int D,
+               const int64_t* codes, int64_t scq, int64_t scb, int64_t sct,
+               int n_q, int B, int T, float* out, void* stream);
+
+/* ---- EMA statistics: bincount + scatter-add of core_vq.py:227-228 for all stages at once.
+ * Re-derives each stage's input residual from x and codes with the encode arithmetic.
+ *   counts     fp32 [n_q, K]     (out; zeroed by the call)  = embed_onehot.sum(0)
+ *   embed_sum  fp32 [n_q, K, D]  (out; zeroed by the call)  = (x^T @ onehot)^T
+ * The caller all-reduces both across ranks (distrib.py:32-34) before rvq_ema_apply.              */
+int rvq_ema_stats(const void* pack, int K, int D,
+                  const float* x, int64_t sxb, int64_t sxd, int64_t sxt, int B, int T,
+                  int stage0, int n_q, const int64_t* codes,
+                  float* counts, float* embed_sum, int flags, void* stream);
+
+/* ---- EMA apply: core_vq.py:227-235 + :49-60 for n_q stages (in-place on the module buffers).
+ * *_ptrs_host: HOST arrays of n_q DEVICE pointers (cluster_size [K], embed_avg [K,D], embed [K,D]). */
+int rvq_ema_apply(float* const* cluster_size_ptrs_host, float* const* embed_avg_ptrs_host,
+                  float* const* embed_ptrs_host, int n_q, int K, int D,
+                  const float* counts, const float* embed_sum,
+                  double decay, double epsilon, void* stream);
+
+/* ---- dead-code expiry: core_vq.py:159-163 (replace_): embed[k] <- samples[k] where
+ * cluster_size[k] < threshold.  samples fp32 [K, D] (rows already drawn by the host RNG).        */
+int rvq_expire_replace(float* embed, const float* cluster_size, const float* samples,
+                       int K, int D, float threshold, void* stream);
+
+/* ---- k-means (core_vq.py:80-102) on flat fp32 samples [N, D] (contiguous).
+ * assign: buckets[n] = argmin_k sum_d (x[n,d]-means[k,d])^2, lowest index on ties (:86-91);
+ *         `pack` is an rvq_pack() image (n_q = 1) of the current means.
+ * update: bins = bincount(buckets); means[k] <- mean of assigned rows, empty clusters keep the
+ *         old mean (:92-100).  sums fp32 [K, D] and bins int64 [K] are caller scratch/outputs.    */
+int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int64_t N,
+                      int64_t* buckets, void* stream);
+int rvq_kmeans_update(const float* samples, int64_t N, int D, const int64_t* buckets, int K,
+                      float* means, int64_t* bins, float* sums, void* stream);
+
+/* ---- backward helper: out[B,T,D] = sum_i w[i] * r_{i+1}, r_{i+1} the residual after stage i,
+ * recomputed from x and codes (gradient of the commitment losses).
+ *   w  fp32 [n_q] DEVICE                                                                         */
+int rvq_residual_combine(const void* pack, int K, int D,
+                         const float* x, int64_t sxb, int64_t sxd, int64_t sxt, int B, int T,
+                         int stage0, int n_q, const int64_t* codes, const float* w,
+                         float* out, int flags, void* stream);
+
+/* ---- debug / evidence: counters of the tcgen05 search written by the last rvq_encode on
+ * `stream`-ordered memory inside the pack: [0] frame-stages searched, [1] certified unique,
+ * [2] re-scored (2..4 candidates), [3] exact full-scan fallbacks.  out_host: 4 x uint64.
+ * Synchronises the stream.                                                                      */
+int rvq_search_stats(const void* pack, uint64_t* out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVQ_B200_H */
