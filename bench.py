@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Headline benchmark: RVQ encode frames/s (n_q=32, codebook 1024x128) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step is one fused encode of BASELINE.json configs[1] (latents [64, 128, 750] fp32, n_q=32,
+bins=1024: 48 000 frames) on every rank (frames are sharded over ranks with no data-path
+collective -> weak scaling).  Prints ONE JSON line (see DESIGN.md "Measurement").
+``--impl reference`` times the reference algorithm's CPU restatement (oracle/, the reference is
+pure Python/PyTorch) on the host cores for the same workload, on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rvq_encode_frames_per_s"
+UNIT = "frames/s"
+B, D, T, NQ, BINS, FRAME_RATE, BW = 64, 128, 750, 32, 1024, 75, 24.0
+FLOP_PER_FRAME_STAGE = 2 * BINS * D          # only the x.c^T contraction counts
+WORKLOAD = f"cfg2: 24 kHz 24 kbps RVQ encode, latents [{B},{D},{T}] fp32, n_q={NQ}, bins={BINS}"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"tflops": float(j["bf16_tflops"]), "tflops_sustained": float(j.get("bf16_tflops_sustained", 0) or 0),
+                "hbm_gbs": float(j["hbm_gbs"]), "source": "measured"}
+    return {"tflops": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated in oracle/ (PyTorch-CPU ops in the reference's order)
+# --------------------------------------------------------------------------------------------
+def _cpu_encode_rate(batch_items: int, reps: int, budget_s: float):
+    from oracle import cases as C
+    from oracle import rvq_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    states = C.codebooks(D, BINS, NQ, 0)
+    x = C.latents(batch_items, D, T, 1234)
+    with torch.no_grad():
+        O.rvq_encode(states, x[:1], NQ)                       # warm-up (thread pool, allocator)
+        times = []
+        t_start = time.perf_counter()
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.rvq_encode(states, x, NQ)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > budget_s:
+                break
+    frames = batch_items * T
+    return frames / statistics.median(times), frames, len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cases as C
+    from oracle import rvq_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    states = C.codebooks(D, BINS, NQ, 0)
+    # size the per-step sample so that a step costs ~0.15 s on this host
+    probe_rate, _, _ = _cpu_encode_rate(1, 2, 5.0)
+    items = max(1, min(B, int(round(probe_rate * 0.15 / T))))
+    x = C.latents(items, D, T, 1234)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 3))):
+            O.rvq_encode(states, x, NQ)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.rvq_encode(states, x, NQ)
+        dt = time.perf_counter() - t0
+    frames = items * T
+    value = frames * args.steps / dt
+    sample = f"{items} of {B} batch items ({frames} frames, n_q={NQ}) per step, oracle port of core_vq.py:357-367"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import encodec_pytorch_b200 as E
+    from encodec_pytorch_b200 import _lib
+    from oracle import cases as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = _peaks()
+
+    torch.manual_seed(0)
+    q = E.ResidualVectorQuantizer(dimension=D, n_q=NQ, bins=BINS, kmeans_init=False).to(dev).eval()
+    # rotating input sets whose footprint exceeds the 126 MB L2, so every step reads its latents from HBM
+    n_sets = 8
+    xs = [C.latents(B, D, T, 1234 + 17 * (rank * n_sets + i)).to(dev) for i in range(n_sets)]
+    set_bytes = xs[0].numel() * 4 + NQ * B * T * 8
+    frames = B * T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(3, args.warmup)):
+            q.encode(xs[i % n_sets], FRAME_RATE, BW)
+        barrier()
+        # ---- device-resident timing (value) with per-launch events for the roofline ------------
+        sampler = ClockSampler(_physical_gpu_index(local))
+        sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        l0 = _lib.launch_count()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for i in range(args.steps):
+            ev[i][0].record()
+            q.encode(xs[i % n_sets], FRAME_RATE, BW)
+            ev[i][1].record()
+        t_end.record()
+        barrier()
+        launches = _lib.launch_count() - l0
+        clocks = sampler.stop()
+        total_ms = t_start.elapsed_time(t_end)
+        kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+
+        # ---- end to end: pinned host latents in, int64 codes back to pinned host, every step -----
+        xh = [C.latents(B, D, T, 99 + i).pin_memory() for i in range(2)]
+        ch = [torch.empty((NQ, B, T), dtype=torch.int64).pin_memory() for _ in range(2)]
+        xd = [torch.empty_like(xs[0]) for _ in range(2)]
+
+        def e2e_step(i):
+            xd[i % 2].copy_(xh[i % 2], non_blocking=True)
+            c = q.encode(xd[i % 2], FRAME_RATE, BW)
+            ch[i % 2].copy_(c, non_blocking=True)
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e_end.record()
+        barrier()
+        e2e_ms = e_start.elapsed_time(e_end)
+
+        # ---- secondary: decode (HBM/L2-bound gather) ---------------------------------------------
+        codes = q.encode(xs[0], FRAME_RATE, BW)
+        for _ in range(3):
+            q.decode(codes)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        d0.record()
+        for _ in range(20):
+            q.decode(codes)
+        d1.record()
+        torch.cuda.synchronize()
+        dec_ms = d0.elapsed_time(d1) / 20
+
+    times = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = (float(v) for v in times.tolist())
+    value = world * frames * args.steps / (total_ms * 1e-3)
+    e2e_value = world * frames * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        achieved = frames * NQ * FLOP_PER_FRAME_STAGE / (kernel_ms * 1e-3) / 1e12
+        cpu_rate, cpu_frames, cpu_reps = _cpu_encode_rate(8, 5, 20.0) if world == 1 else (None, 0, 0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16xf16->f32 search, f32 re-score/residual",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": frames,
+                       "l2": f"{n_sets} rotating input sets x {set_bytes / 1e6:.1f} MB > 126 MB L2",
+                       "codebooks": "kaiming-uniform, torch.manual_seed(0) (reference constructor)",
+                       "parallelism": f"frames sharded over {world} rank(s), no data-path collective"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "kernel": "fused n_q-stage encode (one launch per step)", "kernel_ms": kernel_ms,
+                         "peak_source": peaks["source"] + " burst (kernel timed alone)",
+                         "frac_of_sustained": (achieved / peaks["tflops_sustained"]) if peaks["tflops_sustained"] else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * T * 4,
+                    "d2h_bytes_per_step": NQ * B * T * 8, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "decode": {"frames_per_s": frames / (dec_ms * 1e-3), "ms": dec_ms,
+                       "hbm_gbs": frames * (8 * NQ + 4 * D) / (dec_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]},
+        }
+        if cpu_rate is not None:
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"8 of {B} batch items ({cpu_frames} frames, n_q={NQ}), median of {cpu_reps} "
+                                              "runs of the oracle port of core_vq.py:357-367"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "librvq_b200.so")
 FLAG_STE = 1
 FLAG_FORCE_EXACT = 2
 FLAG_DIRECT_DIST = 4
+FLAG_ACCUM_Q = 8
 
 _lib: tp.Optional[C.CDLL] = None
 
@@ -30,11 +31,12 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "rvq_launch_count": (C.c_uint64, []),
     "rvq_pack_bytes": (_sz, [_i, _i, _i]),
     "rvq_pack": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
-    "rvq_encode": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "rvq_encode": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "rvq_decode": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "rvq_ema_stats": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "rvq_ema_apply": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _dbl, _dbl, _vp]),
     "rvq_expire_replace": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
+    "rvq_expire_codes": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _vp]),
     "rvq_kmeans_assign": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp]),
     "rvq_kmeans_update": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "rvq_residual_combine": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),

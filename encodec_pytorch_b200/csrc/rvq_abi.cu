@@ -78,26 +78,29 @@ int rvq_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* p
 }
 
 int rvq_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
-               int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, double* stage_sqerr,
-               int flags, void* stream) {
+               int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, float* residual_out,
+               double* stage_sqerr, int flags, void* stream) {
   if (int e = check_device()) return e;
   RVQ_REQUIRE(pack, "rvq_encode: null pack");
   RVQ_REQUIRE(B >= 0 && T >= 0 && n_q >= 0 && stage0 >= 0 && K > 0 && D > 0, "rvq_encode: bad shape");
   if (int64_t(B) * T == 0 || n_q == 0) return RVQ_OK;
   RVQ_REQUIRE(x && codes, "rvq_encode: null pointer");
+  RVQ_REQUIRE(int64_t(B) * T < (int64_t(1) << 31), "rvq_encode: more than 2^31 frames in one call");
   cudaStream_t st = (cudaStream_t)stream;
+  EncodeArgs a{pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, residual_out, stage_sqerr, flags};
   const bool want_tc = tc_shape(K, D) && !(flags & (RVQ_FLAG_FORCE_EXACT | RVQ_FLAG_DIRECT_DIST));
-  if (want_tc) return tc_encode(pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, stage_sqerr, flags, st);
-  return simt_encode(pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, stage_sqerr, flags, st);
+  return want_tc ? tc_encode(a, st) : simt_encode(a, st);
 }
 
 int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int64_t N, int64_t* buckets, void* stream) {
   if (int e = check_device()) return e;
   RVQ_REQUIRE(pack && (N == 0 || (samples && buckets)), "rvq_kmeans_assign: null pointer");
   RVQ_REQUIRE(N >= 0 && N < (int64_t(1) << 31), "rvq_kmeans_assign: N out of range");
+  if (N == 0) return RVQ_OK;
   // samples [N, D] viewed as x[B=1, D, T=N] with strides (0, 1, D)
-  return simt_encode(pack, K, D, samples, 0, 1, D, 1, (int)N, 0, 1, buckets, nullptr, nullptr,
-                     RVQ_FLAG_DIRECT_DIST | RVQ_FLAG_FORCE_EXACT, (cudaStream_t)stream);
+  EncodeArgs a{pack, K, D, samples, 0, 1, D, 1, (int)N, 0, 1, buckets, nullptr, nullptr, nullptr,
+               RVQ_FLAG_DIRECT_DIST | RVQ_FLAG_FORCE_EXACT};
+  return simt_encode(a, (cudaStream_t)stream);
 }
 
 int rvq_search_stats(const void* pack, uint64_t* out_host, void* stream) {

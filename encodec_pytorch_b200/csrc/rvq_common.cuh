@@ -100,12 +100,15 @@ struct FrameAddr {
 };
 
 // ---- entry points implemented per translation unit -------------------------------------------
+struct EncodeArgs {
+  const void* pack; int K, D;
+  const float* x; int64_t sxb, sxd, sxt; int B, T;
+  int stage0, n_q;
+  int64_t* codes; float* quantized; float* residual_out; double* sqerr;
+  int flags;
+};
 int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st);
-int simt_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
-                int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, double* sqerr,
-                int flags, cudaStream_t st);
-int tc_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
-              int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, double* sqerr,
-              int flags, cudaStream_t st);
+int simt_encode(const EncodeArgs& a, cudaStream_t st);
+int tc_encode(const EncodeArgs& a, cudaStream_t st);
 
 }  // namespace rvq

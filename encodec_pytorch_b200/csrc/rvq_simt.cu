@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(256, 2)
 exact_encode_kernel(const unsigned char* pack, int K, int D,
                     const float* __restrict__ x, FrameAddr fa, int64_t N,
                     int stage0, int n_q, int64_t* __restrict__ codes,
-                    float* __restrict__ quantized, double* __restrict__ sqerr, int ste) {
+                    float* __restrict__ quantized, float* __restrict__ residual_out,
+                    double* __restrict__ sqerr, int ste, int accum_q) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                    // [D][64] residual, frame-contiguous
   float* cs = xs + size_t(D) * kXF;    // [D][64] codebook chunk, code-contiguous
@@ -217,8 +218,16 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
     }
     xpart[uq * kXF + uf] = part;
   }
-  if (quantized != nullptr)
-    for (int d = uq * dq; d < (uq + 1) * dq; ++d) qs[d * kXF + uf] = 0.f;
+  if (quantized != nullptr) {
+    if (accum_q) {
+      for (int i = tid; i < kXF * D; i += 256) {
+        int f = i / D, d = i - f * D;
+        qs[d * kXF + f] = (n0 + f < N) ? quantized[(n0 + f) * D + d] : 0.f;
+      }
+    } else {
+      for (int d = uq * dq; d < (uq + 1) * dq; ++d) qs[d * kXF + uf] = 0.f;
+    }
+  }
   __syncthreads();
   if (tid < kXF) xx[tid] = ((xpart[tid] + xpart[kXF + tid]) + xpart[2 * kXF + tid]) + xpart[3 * kXF + tid];
 
@@ -321,31 +330,37 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
       atomicAdd(&sqerr[si], t);
     }
   }
+  __syncthreads();
+  // frame-major stores: consecutive threads write consecutive dims of one frame
   if (quantized != nullptr) {
-    __syncthreads();
-    // frame-major store: consecutive threads write consecutive dims of one frame
     for (int i = tid; i < kXF * D; i += 256) {
       int f = i / D, d = i - f * D;
       if (n0 + f < N) quantized[(n0 + f) * D + d] = qs[d * kXF + f];
     }
   }
+  if (residual_out != nullptr) {
+    for (int i = tid; i < kXF * D; i += 256) {
+      int f = i / D, d = i - f * D;
+      if (n0 + f < N) residual_out[(n0 + f) * D + d] = xs[d * kXF + f];
+    }
+  }
 }
 
-int simt_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
-                int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, double* sqerr,
-                int flags, cudaStream_t st) {
+int simt_encode(const EncodeArgs& a, cudaStream_t st) {
+  const int K = a.K, D = a.D;
   RVQ_REQUIRE(D % 4 == 0 && D >= 4 && D <= 256, "rvq_encode: dimension %d unsupported (multiple of 4, <= 256)", D);
   RVQ_REQUIRE(K >= 1, "rvq_encode: codebook_size %d", K);
-  const int64_t N = int64_t(B) * T;
-  if (N == 0 || n_q == 0) return RVQ_OK;
-  size_t smem = (size_t(D) * (kXF + kXC + (quantized ? kXF : 0)) + kXF + 4 * kXF + kXF + 8) * 4;
-  FrameAddr fa{sxb, sxd, sxt, T};
+  const int64_t N = int64_t(a.B) * a.T;
+  if (N == 0 || a.n_q == 0) return RVQ_OK;
+  size_t smem = (size_t(D) * (kXF + kXC + (a.quantized ? kXF : 0)) + kXF + 4 * kXF + kXF + 8) * 4;
+  FrameAddr fa{a.sxb, a.sxd, a.sxt, a.T};
   unsigned grid = unsigned((N + kXF - 1) / kXF);
-  const bool direct = (flags & RVQ_FLAG_DIRECT_DIST) != 0;
+  const bool direct = (a.flags & RVQ_FLAG_DIRECT_DIST) != 0;
   auto kern = direct ? exact_encode_kernel<true> : exact_encode_kernel<false>;
   RVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, 256, smem, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0, n_q, codes, quantized,
-                                sqerr, (flags & RVQ_FLAG_STE) ? 1 : 0);
+  kern<<<grid, 256, smem, st>>>((const unsigned char*)a.pack, K, D, a.x, fa, N, a.stage0, a.n_q, a.codes,
+                                a.quantized, a.residual_out, a.sqerr, (a.flags & RVQ_FLAG_STE) ? 1 : 0,
+                                (a.flags & RVQ_FLAG_ACCUM_Q) ? 1 : 0);
   RVQ_LAUNCH_CHECK("exact_encode_kernel");
   return RVQ_OK;
 }
@@ -480,6 +495,31 @@ __global__ void expire_replace_kernel(float* embed, const float* __restrict__ cl
   if (i < K * D && cluster_size[i / D] < thr) embed[i] = samples[i];
 }
 
+// one warp per code k: if the code is dead, walk the selected frame's residual chain up to `stage`
+__global__ void __launch_bounds__(256)
+expire_codes_kernel(const unsigned char* pack, int K, int D, const float* __restrict__ x, rvq::FrameAddr fa,
+                    int64_t N, int stage0, int stage, const int64_t* __restrict__ codes,
+                    const int64_t* __restrict__ sel, const float* __restrict__ cluster_size, float thr,
+                    float* __restrict__ embed, int ste) {
+  rvq::PackView pv(pack, K, D);
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= K || !(cluster_size[k] < thr)) return;
+  int64_t n = sel[k];
+  n = n < 0 ? 0 : (n >= N ? N - 1 : n);
+  for (int d = lane; d < D; d += 32) {
+    float r = x[fa.base(n) + int64_t(d) * fa.sxd];
+    for (int i = 0; i < stage; ++i) {
+      int64_t c = codes[int64_t(i) * N + n];
+      int idx = c < 0 ? 0 : (c >= K ? K - 1 : int(c));
+      float q = pv.tab32(stage0 + i)[size_t(idx) * D + d];
+      if (ste) q = r + (q - r);
+      r -= q;
+    }
+    embed[size_t(k) * D + d] = r;
+  }
+}
+
 __global__ void kmeans_scatter_kernel(const float* __restrict__ samples, int64_t N, int D,
                                       const int64_t* __restrict__ buckets, int K,
                                       float* sums, unsigned long long* bins) {
@@ -511,10 +551,10 @@ extern "C" {
 int rvq_decode(const void* pack, int K, int D, const int64_t* codes, int64_t scq, int64_t scb, int64_t sct,
                int n_q, int B, int T, float* out, void* stream) {
   if (int e = check_device()) return e;
-  RVQ_REQUIRE(pack && out && (codes || n_q == 0), "rvq_decode: null pointer");
   RVQ_REQUIRE(D % 4 == 0 && D > 0 && K > 0 && n_q >= 0 && B >= 0 && T >= 0, "rvq_decode: bad shape K=%d D=%d n_q=%d", K, D, n_q);
   const int64_t N = int64_t(B) * T;
   if (N == 0) return RVQ_OK;
+  RVQ_REQUIRE(pack && out && (codes || n_q == 0), "rvq_decode: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   FrameAddr fa{0, 0, 0, T};
   chain_kernel<kDecode><<<chain_grid(N), 256, 0, st>>>((const unsigned char*)pack, K, D, nullptr, fa, N, 0, n_q,
@@ -592,6 +632,22 @@ int rvq_expire_replace(float* embed, const float* cluster_size, const float* sam
   int n = K * D;
   expire_replace_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(embed, cluster_size, samples, K, D, threshold);
   RVQ_LAUNCH_CHECK("expire_replace_kernel");
+  return RVQ_OK;
+}
+
+int rvq_expire_codes(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+                     int B, int T, int stage0, int stage, const int64_t* codes, const int64_t* sel,
+                     const float* cluster_size, float threshold, float* embed, int flags, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(pack && x && sel && cluster_size && embed && (codes || stage == 0), "rvq_expire_codes: null pointer");
+  RVQ_REQUIRE(K > 0 && D > 0 && stage >= 0 && stage0 >= 0, "rvq_expire_codes: bad shape");
+  const int64_t N = int64_t(B) * T;
+  RVQ_REQUIRE(N > 0, "rvq_expire_codes: empty batch");
+  FrameAddr fa{sxb, sxd, sxt, T};
+  expire_codes_kernel<<<(K + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)pack, K, D, x, fa, N, stage0,
+                                                                     stage, codes, sel, cluster_size, threshold, embed,
+                                                                     (flags & RVQ_FLAG_STE) ? 1 : 0);
+  RVQ_LAUNCH_CHECK("expire_codes_kernel");
   return RVQ_OK;
 }
 

@@ -1,0 +1,491 @@
+"""Host-side mirror of the reference's ``quantization/core_vq.py`` for the B200 RVQ path.
+
+Same classes, constructor arguments, buffer names and ``state_dict`` keys as
+the reference (``EuclideanCodebook`` core_vq.py:105-237, ``VectorQuantization``
+:240-324, ``ResidualVectorQuantization`` :327-375, helpers :45-102), but every
+arithmetic step runs in the hand-written sm_100a kernels behind the C ABI
+(``include/rvq_b200.h``) -- a residual stack is ONE fused launch instead of the
+reference's per-stage ATen loop.  CUDA fp32 tensors only: anything else raises
+(no CPU fallback, no other backend).
+"""
+from __future__ import annotations
+
+import typing as tp
+import warnings
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import _ops as ops
+from .. import distrib
+
+
+def default(val: tp.Any, d: tp.Any) -> tp.Any:
+    """core_vq.py:45-46."""
+    return val if val is not None else d
+
+
+def ema_inplace(moving_avg: torch.Tensor, new: torch.Tensor, decay: float) -> None:
+    """core_vq.py:49-56 (kept for API parity; the stack update runs in ``rvq_ema_apply``)."""
+    moving_avg.data.mul_(decay).add_(new, alpha=(1 - decay))
+
+
+def laplace_smoothing(x: torch.Tensor, n_categories: int, epsilon: float = 1e-5) -> torch.Tensor:
+    """core_vq.py:59-60."""
+    return (x + epsilon) / (x.sum() + n_categories * epsilon)
+
+
+def uniform_init(*shape: int) -> torch.Tensor:
+    """core_vq.py:63-66."""
+    t = torch.empty(shape)
+    nn.init.kaiming_uniform_(t)
+    return t
+
+
+def sample_indices(num_samples: int, num: int, device: torch.device) -> torch.Tensor:
+    """Index draw of core_vq.py:69-77: ``randperm`` prefix, or ``randint`` with replacement when
+    there are fewer samples than requested.  Consumes the device's global torch RNG like the
+    reference does."""
+    if num_samples >= num:
+        return torch.randperm(num_samples, device=device)[:num]
+    return torch.randint(0, num_samples, (num,), device=device)
+
+
+def sample_vectors(samples: torch.Tensor, num: int) -> torch.Tensor:
+    """core_vq.py:69-77."""
+    return samples[sample_indices(samples.shape[0], num, samples.device)]
+
+
+def kmeans(samples: torch.Tensor, num_clusters: int, num_iters: int = 10,
+           init_means: tp.Optional[torch.Tensor] = None) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+    """core_vq.py:80-102: Lloyd iterations on flat ``[N, D]`` samples.  Assignment (direct
+    sum-of-squared-differences, lowest index on ties) and the bincount / scatter-add centroid
+    update (empty clusters keep their mean) are the ``rvq_kmeans_*`` kernels.  ``init_means``
+    lets a caller inject the starting centroids instead of drawing them."""
+    L.require_cuda_f32(samples, "kmeans samples")
+    samples = samples.contiguous()
+    means = (sample_vectors(samples, num_clusters) if init_means is None else init_means).contiguous().clone()
+    bins = torch.zeros(num_clusters, dtype=torch.int64, device=samples.device)
+    for _ in range(num_iters):
+        pk = ops.pack([means])
+        buckets = ops.kmeans_assign(pk, samples)
+        bins = ops.kmeans_update(samples, buckets, means)
+    return means, bins
+
+
+def _flat_as_bdt(flat: torch.Tensor) -> torch.Tensor:
+    """``[N, D]`` contiguous frames as the ``[1, D, N]`` strided view the kernels take."""
+    return flat.t().unsqueeze(0)
+
+
+class EuclideanCodebook(nn.Module):
+    """Codebook with Euclidean distance (core_vq.py:105-237); see the reference for the argument
+    documentation.  Buffers: ``inited [1]``, ``cluster_size [K]``, ``embed [K, D]``,
+    ``embed_avg [K, D]`` (all fp32)."""
+
+    def __init__(self, dim: int, codebook_size: int, kmeans_init: int = False, kmeans_iters: int = 10,
+                 decay: float = 0.99, epsilon: float = 1e-5, threshold_ema_dead_code: int = 2):
+        super().__init__()
+        self.decay = decay
+        init_fn: tp.Union[tp.Callable[..., torch.Tensor], tp.Any] = uniform_init if not kmeans_init else torch.zeros
+        embed = init_fn(codebook_size, dim)
+
+        self.codebook_size = codebook_size
+        self.kmeans_iters = kmeans_iters
+        self.epsilon = epsilon
+        self.threshold_ema_dead_code = threshold_ema_dead_code
+
+        self.register_buffer("inited", torch.Tensor([not kmeans_init]))
+        self.register_buffer("cluster_size", torch.zeros(codebook_size))
+        self.register_buffer("embed", embed)
+        self.register_buffer("embed_avg", embed.clone())
+
+        # host-side caches (not state): inited flag without a device sync, search image of `embed`
+        self._inited_host: tp.Optional[bool] = None
+        self._gen = 0
+        self._pack_cache: tp.Optional[tp.Tuple[tp.Any, ops.CodebookPack]] = None
+        # test hook: starting centroids for the next k-means init (instead of the RNG draw)
+        self._kmeans_init_means: tp.Optional[torch.Tensor] = None
+
+    # ---- cache management ---------------------------------------------------------------------
+    def invalidate(self) -> None:
+        """Forget host-side caches; call after mutating ``embed`` / ``inited`` through ``.data``."""
+        self._gen += 1
+        self._pack_cache = None
+        self._inited_host = None
+
+    def _tables_changed(self) -> None:
+        self._gen += 1
+        self._pack_cache = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate()
+
+    def _is_inited(self) -> bool:
+        """``if self.inited`` of core_vq.py:148 with the device read cached on the host."""
+        if self._inited_host is None:
+            self._inited_host = bool(self.inited.item())
+        return self._inited_host
+
+    def _key(self):
+        return (self.embed.data_ptr(), self.embed._version, self._gen)
+
+    def _pack(self) -> ops.CodebookPack:
+        key = self._key()
+        if self._pack_cache is None or self._pack_cache[0] != key:
+            self._pack_cache = (key, ops.pack([self.embed]))
+        return self._pack_cache[1]
+
+    # ---- reference API ------------------------------------------------------------------------
+    @torch.jit.ignore
+    def init_embed_(self, data: torch.Tensor) -> None:
+        """core_vq.py:146-157: k-means on the first batch; then (the step the reference left as a
+        FIXME) broadcast the initialised buffers from rank 0 so all ranks start in sync."""
+        if self._is_inited():
+            return
+        L.require_cuda_f32(data, "init_embed_ data")
+        with torch.no_grad():
+            embed, cluster_size = kmeans(data, self.codebook_size, self.kmeans_iters, self._kmeans_init_means)
+            self._kmeans_init_means = None
+            self.embed.data.copy_(embed)
+            self.embed_avg.data.copy_(embed.clone())
+            self.cluster_size.data.copy_(cluster_size)
+            self.inited.data.copy_(torch.Tensor([True]))
+            distrib.broadcast_tensors(self.buffers())
+        self._inited_host = True
+        self._tables_changed()
+
+    def replace_(self, samples: torch.Tensor, mask: torch.Tensor) -> None:
+        """core_vq.py:159-163."""
+        picked = sample_vectors(samples, self.codebook_size)
+        with torch.no_grad():
+            self.embed.data.copy_(torch.where(mask[..., None], picked, self.embed))
+        self._tables_changed()
+
+    def expire_codes_(self, batch_samples: torch.Tensor) -> None:
+        """core_vq.py:165-175: rows whose EMA cluster size fell below the threshold are replaced by
+        random batch rows (``rvq_expire_replace``).  ``torch.any`` is a host sync, as upstream."""
+        if self.threshold_ema_dead_code == 0:
+            return
+        expired = self.cluster_size < self.threshold_ema_dead_code
+        if not torch.any(expired):
+            return
+        flat = batch_samples.reshape(-1, batch_samples.shape[-1])
+        picked = sample_vectors(flat, self.codebook_size)
+        ops.expire_replace(self.embed, self.cluster_size, picked, float(self.threshold_ema_dead_code))
+        self._tables_changed()
+
+    def preprocess(self, x: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:177-179."""
+        return x.reshape(-1, x.shape[-1])
+
+    def quantize(self, x: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:181-189 on flat ``[N, D]`` frames: index of the nearest code."""
+        L.require_cuda_f32(x, "quantize input")
+        flat = x.contiguous()
+        codes, _, _, _ = ops.encode(self._pack(), _flat_as_bdt(flat), 0, 1)
+        return codes.view(-1)
+
+    def postprocess_emb(self, embed_ind: torch.Tensor, shape) -> torch.Tensor:
+        """core_vq.py:191-192."""
+        return embed_ind.view(*shape[:-1])
+
+    def dequantize(self, embed_ind: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:194-196: table gather (``rvq_decode`` with one stage)."""
+        shape = tuple(embed_ind.shape)
+        out = ops.decode(self._pack(), embed_ind.reshape(1, 1, -1))
+        return out.view(*shape, self.embed.shape[1])
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:198-206."""
+        shape = x.shape
+        return self.postprocess_emb(self.quantize(self.preprocess(x)), shape)
+
+    def decode(self, embed_ind: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:208-210."""
+        return self.dequantize(embed_ind)
+
+    def forward(self, x: torch.Tensor) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+        """core_vq.py:212-237: init if needed, search + gather with the PRE-update table, then (in
+        training) expiry and the EMA update."""
+        shape = x.shape
+        L.require_cuda_f32(x, "codebook input")
+        flat = self.preprocess(x.detach()).contiguous()
+        self.init_embed_(flat)
+        pk = self._pack()
+        codes, quant, _, _ = ops.encode(pk, _flat_as_bdt(flat), 0, 1, want_quantized=True)
+        embed_ind = self.postprocess_emb(codes.view(-1), shape)
+        quantize = quant.view(*shape)
+        if self.training:
+            with torch.no_grad():
+                self.expire_codes_(flat)
+                _update_stack([self], pk, _flat_as_bdt(flat), codes, 0, flags=0)
+        return quantize, embed_ind
+
+
+def _update_stack(codebooks: tp.Sequence[EuclideanCodebook], pk: ops.CodebookPack, x_bdt: torch.Tensor,
+                  codes: torch.Tensor, stage0: int, flags: int) -> None:
+    """EMA update of core_vq.py:227-235 for a run of stages at once: bincount + per-code residual
+    sums (``rvq_ema_stats``), ONE all-reduce of the packed statistics across the frame shards
+    (the role of distrib.all_reduce, distrib.py:32-34), then EMA / Laplace smoothing / table
+    overwrite in place (``rvq_ema_apply``)."""
+    flat, counts, esum = ops.ema_stats(pk, x_bdt, codes, stage0, flags)
+    distrib.all_reduce_stats(flat)
+    cb0 = codebooks[0]
+    ops.ema_apply([cb.cluster_size for cb in codebooks], [cb.embed_avg for cb in codebooks],
+                  [cb.embed for cb in codebooks], counts, esum, cb0.decay, cb0.epsilon)
+    for cb in codebooks:
+        cb._tables_changed()
+
+
+class _AttachGrad(torch.autograd.Function):
+    """Wires the already computed training outputs into autograd with the reference's gradient
+    (SURVEY.md 3.4-6): every stage's straight-through term passes identity and residuals subtract
+    detached values, so ``d quantized / d x = n_q * I``; ``d loss_i / d x = 2 w (r_i - ste_i) / n``
+    (core_vq.py:309, :319-320, :348-349).  The residuals are recomputed from ``x`` and the codes
+    with the pre-update tables held by ``pk`` (``rvq_residual_combine``)."""
+
+    @staticmethod
+    def forward(ctx, x, quantized, losses, codes, pk, n_q, commitment_weight, flags):
+        ctx.save_for_backward(x, codes)
+        ctx.pk, ctx.n_q, ctx.cw, ctx.flags = pk, n_q, commitment_weight, flags
+        return quantized.view_as(quantized), losses.view_as(losses)
+
+    @staticmethod
+    def backward(ctx, g_quantized, g_losses):
+        x, codes = ctx.saved_tensors
+        grad = None
+        if g_quantized is not None:
+            grad = g_quantized * float(ctx.n_q)
+        if g_losses is not None and ctx.cw > 0:
+            b, d, t = x.shape
+            w = g_losses.reshape(-1).to(torch.float32) * (2.0 * ctx.cw / float(b * t * d))
+            comb = ops.residual_combine(ctx.pk, x, codes, 0, w, ctx.flags).permute(0, 2, 1)
+            grad = comb if grad is None else grad + comb
+        return grad, None, None, None, None, None, None, None
+
+
+class VectorQuantization(nn.Module):
+    """Vector quantization (core_vq.py:240-324); only Euclidean distance, like the reference."""
+
+    def __init__(self, dim: int, codebook_size: int, codebook_dim: tp.Optional[int] = None, decay: float = 0.99,
+                 epsilon: float = 1e-5, kmeans_init: bool = True, kmeans_iters: int = 50,
+                 threshold_ema_dead_code: int = 2, commitment_weight: float = 1.):
+        super().__init__()
+        _codebook_dim: int = default(codebook_dim, dim)
+        requires_projection = _codebook_dim != dim
+        self.project_in = (nn.Linear(dim, _codebook_dim) if requires_projection else nn.Identity())
+        self.project_out = (nn.Linear(_codebook_dim, dim) if requires_projection else nn.Identity())
+        self.epsilon = epsilon
+        self.commitment_weight = commitment_weight
+        self._codebook = EuclideanCodebook(dim=_codebook_dim, codebook_size=codebook_size,
+                                           kmeans_init=kmeans_init, kmeans_iters=kmeans_iters,
+                                           decay=decay, epsilon=epsilon,
+                                           threshold_ema_dead_code=threshold_ema_dead_code)
+        self.codebook_size = codebook_size
+
+    @property
+    def codebook(self) -> torch.Tensor:
+        return self._codebook.embed
+
+    @property
+    def _plain(self) -> bool:
+        return isinstance(self.project_in, nn.Identity) and isinstance(self.project_out, nn.Identity)
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:289-293: ``[B, D, T]`` -> ``[B, T]`` int64."""
+        if self._plain:
+            L.require_cuda_f32(x, "x")
+            codes, _, _, _ = ops.encode(self._codebook._pack(), x, 0, 1)
+            return codes[0]
+        return self._codebook.encode(self.project_in(x.permute(0, 2, 1)))
+
+    def decode(self, embed_ind: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:295-299: ``[B, T]`` -> ``[B, D, T]`` (a permuted ``[B, T, D]`` buffer)."""
+        quantize = self._codebook.decode(embed_ind)
+        quantize = self.project_out(quantize)
+        return quantize.permute(0, 2, 1)
+
+    def forward(self, x: torch.Tensor):
+        """core_vq.py:301-324: returns ``(quantize [B, D, T], embed_ind [B, T], loss [1])``."""
+        if self._plain:
+            quantized, codes, losses = _stack_forward([self], x, 1, self.training)
+            return quantized, codes[0], losses[0]
+        # projected codebooks (never built by the EnCodec models): per-op path around the kernels
+        device = x.device
+        xp = self.project_in(x.permute(0, 2, 1))
+        quantize, embed_ind = self._codebook(xp)
+        if self.training:
+            quantize = xp + (quantize - xp).detach()
+        loss = torch.tensor([0.0], device=device, requires_grad=self.training)
+        if self.training:
+            _warn_issue25()
+            if self.commitment_weight > 0:
+                loss = loss + torch.nn.functional.mse_loss(quantize.detach(), xp) * self.commitment_weight
+        quantize = self.project_out(quantize).permute(0, 2, 1)
+        return quantize, embed_ind, loss
+
+
+def _warn_issue25() -> None:
+    warnings.warn('When using RVQ in training model, first check '
+                  'https://github.com/facebookresearch/encodec/issues/25 . '
+                  'The bug wasn\'t fixed here for reproducibility.')
+
+
+def _expire_stack(layers: tp.Sequence[VectorQuantization], pk: ops.CodebookPack, x: torch.Tensor,
+                  codes: torch.Tensor, stage0: int, flags: int) -> None:
+    """Dead-code expiry (core_vq.py:165-175) for a run of stages: one host read of the per-stage
+    "any code below threshold" flags (the reference syncs once per stage), then for each firing
+    stage, in stage order, the reference's index draw and ``rvq_expire_codes``."""
+    cbs = [l._codebook for l in layers]
+    thr = cbs[0].threshold_ema_dead_code
+    if thr == 0:
+        return
+    flags_host = torch.stack([(cb.cluster_size < thr).any() for cb in cbs]).tolist()
+    b, _, t = x.shape
+    for i, (cb, fire) in enumerate(zip(cbs, flags_host)):
+        if not fire:
+            continue
+        sel = sample_indices(b * t, cb.codebook_size, x.device).contiguous()
+        ops.expire_codes(pk, x, codes, stage0, i, sel, cb.cluster_size, float(thr), cb.embed, flags)
+        cb._tables_changed()
+
+
+def _stack_forward(layers: tp.Sequence[VectorQuantization], x: torch.Tensor, n_q: int, training: bool,
+                   stack_pack: tp.Optional[tp.Callable[[], ops.CodebookPack]] = None):
+    """Forward of a residual stack of plain (un-projected) layers: core_vq.py:337-355 over
+    :301-324 over :212-237.  Steady state is one fused launch for all ``n_q`` stages; a stage
+    whose codebook still needs its k-means init forces that step to run stage by stage
+    (SURVEY.md 3.4-9).  Returns ``(quantized [B, D, T], codes [n_q, B, T], losses [n_q, 1])``."""
+    L.require_cuda_f32(x, "x")
+    if x.dim() != 3:
+        raise RuntimeError(f"expected x of shape [B, D, T], got {tuple(x.shape)}")
+    layers = list(layers[:n_q])
+    n_q = len(layers)
+    cbs = [l._codebook for l in layers]
+    cw = float(layers[0].commitment_weight)
+    xd = x.detach()
+    b, d, t = xd.shape
+    flags = L.FLAG_STE if training else 0
+    if training:
+        _warn_issue25()
+
+    if all(cb._is_inited() for cb in cbs):
+        pk = stack_pack() if stack_pack is not None else ops.pack([cb.embed for cb in cbs])
+        codes, quant, sqerr, _ = ops.encode(pk, xd, 0, n_q, want_quantized=True,
+                                            want_sqerr=training and cw > 0, flags=flags)
+        if training:
+            with torch.no_grad():
+                _expire_stack(layers, pk, xd, codes, 0, flags)
+                _update_stack(cbs, pk, xd, codes, 0, flags)
+    else:
+        # first step(s): stage i's init needs stage i-1's fresh quantisation -> sequential
+        quant = torch.zeros((b, t, d), dtype=torch.float32, device=x.device)
+        res = xd
+        code_list, sq_list, snap = [], [], []
+        for cb in cbs:
+            if not cb._is_inited():
+                cb.init_embed_(res.permute(0, 2, 1).reshape(b * t, d))
+            pk_i = cb._pack()
+            snap.append(cb.embed.clone() if training else cb.embed)
+            c_i, _, sq_i, res_next = ops.encode(pk_i, res, 0, 1, quantized_accum=quant,
+                                                want_sqerr=training and cw > 0, want_residual=True, flags=flags)
+            if training:
+                with torch.no_grad():
+                    cb.expire_codes_(res.permute(0, 2, 1).reshape(b * t, d))
+                    _update_stack([cb], pk_i, res, c_i, 0, flags)
+            res = res_next.permute(0, 2, 1)
+            code_list.append(c_i)
+            sq_list.append(sq_i)
+        codes = torch.cat(code_list, 0)
+        sqerr = torch.cat(sq_list, 0) if sq_list[0] is not None else None
+        pk = ops.pack(snap) if (training and x.requires_grad) else None
+
+    if training and cw > 0:
+        losses = (sqerr / float(b * t * d)).to(torch.float32).mul_(cw).view(n_q, 1)
+    else:
+        losses = torch.zeros((n_q, 1), dtype=torch.float32, device=x.device)
+    quantized = quant.permute(0, 2, 1)
+    if training:
+        if x.requires_grad and torch.is_grad_enabled():
+            quantized, losses = _AttachGrad.apply(x, quantized, losses, codes, pk, n_q, cw, flags)
+        else:
+            losses.requires_grad_(torch.is_grad_enabled())
+    return quantized, codes, losses
+
+
+class ResidualVectorQuantization(nn.Module):
+    """Residual vector quantization (core_vq.py:327-375): Algorithm 1 of SoundStream, with the
+    whole ``n_q``-stage loop fused into one kernel launch per call."""
+
+    def __init__(self, *, num_quantizers, **kwargs):
+        super().__init__()
+        self.layers = nn.ModuleList([VectorQuantization(**kwargs) for _ in range(num_quantizers)])
+        self._pack_cache: tp.Optional[tp.Tuple[tp.Any, ops.CodebookPack]] = None
+
+    def _fusable(self, n: int) -> bool:
+        return all(l._plain for l in self.layers[:n])
+
+    def _stack_pack(self) -> ops.CodebookPack:
+        """Search image of ALL stages (a prefix serves any ``n_q``), cached until a table changes."""
+        key = tuple(l._codebook._key() for l in self.layers)
+        if self._pack_cache is None or self._pack_cache[0] != key:
+            self._pack_cache = (key, ops.pack([l._codebook.embed for l in self.layers]))
+        return self._pack_cache[1]
+
+    def invalidate(self) -> None:
+        for l in self.layers:
+            l._codebook.invalidate()
+        self._pack_cache = None
+
+    def forward(self, x: torch.Tensor, n_q: tp.Optional[int] = None):
+        """core_vq.py:337-355."""
+        n_q = n_q or len(self.layers)
+        n_q = min(n_q, len(self.layers))           # the reference's slice caps silently (:346)
+        if self._fusable(n_q):
+            return _stack_forward(self.layers, x, n_q, self.training, self._stack_pack)
+        quantized_out = 0.0
+        residual = x
+        all_losses, all_indices = [], []
+        for layer in self.layers[:n_q]:
+            quantized, indices, loss = layer(residual)
+            residual = residual - quantized.detach()
+            quantized_out = quantized_out + quantized
+            all_indices.append(indices)
+            all_losses.append(loss)
+        out_losses, out_indices = map(torch.stack, (all_losses, all_indices))
+        return quantized_out, out_indices, out_losses
+
+    def encode(self, x: torch.Tensor, n_q: tp.Optional[int] = None) -> torch.Tensor:
+        """core_vq.py:357-367: ``[B, D, T]`` fp32 -> ``[n_q, B, T]`` int64."""
+        n_q = n_q or len(self.layers)
+        n_q = min(n_q, len(self.layers))
+        if self._fusable(n_q):
+            L.require_cuda_f32(x, "x")
+            codes, _, _, _ = ops.encode(self._stack_pack(), x.detach(), 0, n_q)
+            return codes
+        residual = x
+        all_indices = []
+        for layer in self.layers[:n_q]:
+            indices = layer.encode(residual)
+            residual = residual - layer.decode(indices)
+            all_indices.append(indices)
+        return torch.stack(all_indices)
+
+    def decode(self, q_indices: torch.Tensor) -> torch.Tensor:
+        """core_vq.py:369-375: ``[n_q, B, T]`` int64 (any strides, any stage prefix) ->
+        ``[B, D, T]`` fp32, stages summed in order."""
+        n = int(q_indices.shape[0])
+        if self._fusable(n):
+            return ops.decode(self._stack_pack(), q_indices).permute(0, 2, 1)
+        quantized_out = torch.tensor(0.0, device=q_indices.device)
+        for i, indices in enumerate(q_indices):
+            quantized_out = quantized_out + self.layers[i].decode(indices)
+        return quantized_out

@@ -38,10 +38,11 @@ extern "C" {
 #define RVQ_ECUDA    -3   /* CUDA runtime error (message has the detail)   */
 #define RVQ_ESIZE    -4   /* caller buffer too small                       */
 
-/* rvq_encode / rvq_ema_stats / rvq_residual_combine flags */
+/* rvq_encode / rvq_ema_stats / rvq_residual_combine / rvq_expire_codes flags */
 #define RVQ_FLAG_STE          1  /* training arithmetic of core_vq.py:309/:348: q <- r + (q - r) */
 #define RVQ_FLAG_FORCE_EXACT  2  /* use the fp32 SIMT search even where the tcgen05 path applies   */
 #define RVQ_FLAG_DIRECT_DIST  4  /* k-means distance sum((x-c)^2) of core_vq.py:86-91 (exact path)  */
+#define RVQ_FLAG_ACCUM_Q      8  /* `quantized` holds a running sum on entry (stage segments)       */
 
 int         rvq_version(void);                 /* RVQ_ABI_VERSION                                    */
 const char* rvq_last_error(void);              /* last error message of the calling thread           */
@@ -65,12 +66,14 @@ int    rvq_pack(const float* const* embed_ptrs_host, int n_q, int K, int D,
  *   codes        int64 [n_q, B, T] contiguous (out)
  *   quantized    fp32 [B, T, D] contiguous (out) or NULL: sum over stages, in stage order, of the
  *                gathered codewords (of the straight-through values with RVQ_FLAG_STE)
+ *                (RVQ_FLAG_ACCUM_Q: added onto the values already in the buffer)
+ *   residual_out fp32 [B, T, D] contiguous (out) or NULL: the residual after the last stage
  *   stage_sqerr  double [n_q] (out, accumulated by atomics; caller zeroes) or NULL:
  *                sum over frames and dims of (q_i - r_i)^2 -> commitment loss numerator (:319)   */
 int rvq_encode(const void* pack, int K, int D,
                const float* x, int64_t sxb, int64_t sxd, int64_t sxt, int B, int T,
                int stage0, int n_q,
-               int64_t* codes, float* quantized, double* stage_sqerr,
+               int64_t* codes, float* quantized, float* residual_out, double* stage_sqerr,
                int flags, void* stream);
 
 /* ---- decode: replaces ResidualVectorQuantization.decode (core_vq.py:369-375).
@@ -101,6 +104,16 @@ int rvq_ema_apply(float* const* cluster_size_ptrs_host, float* const* embed_avg_
  * cluster_size[k] < threshold.  samples fp32 [K, D] (rows already drawn by the host RNG).        */
 int rvq_expire_replace(float* embed, const float* cluster_size, const float* samples,
                        int K, int D, float threshold, void* stream);
+
+/* ---- fused expiry for stage `stage` (relative to stage0) of a residual stack (core_vq.py:165-175):
+ * embed[k] <- r_stage[sel[k]] where cluster_size[k] < threshold; r_stage is the input residual of
+ * that stage, recomputed from x and codes for the K selected frames only.
+ *   sel  int64 [K] DEVICE: frame numbers in [0, B*T) drawn by the host RNG (sample_vectors, :69-77) */
+int rvq_expire_codes(const void* pack, int K, int D,
+                     const float* x, int64_t sxb, int64_t sxd, int64_t sxt, int B, int T,
+                     int stage0, int stage, const int64_t* codes, const int64_t* sel,
+                     const float* cluster_size, float threshold, float* embed,
+                     int flags, void* stream);
 
 /* ---- k-means (core_vq.py:80-102) on flat fp32 samples [N, D] (contiguous).
  * assign: buckets[n] = argmin_k sum_d (x[n,d]-means[k,d])^2, lowest index on ties (:86-91);
