@@ -222,7 +222,9 @@ def residual_combine(pk: CodebookPack, x: torch.Tensor, codes: torch.Tensor, sta
 def search_stats(pk: CodebookPack) -> tp.Dict[str, int]:
     import ctypes as C
     lib = L.load()
-    arr = (C.c_uint64 * 4)()
+    arr = (C.c_uint64 * 16)()
     with _guard(pk.device):
         L.check(lib.rvq_search_stats(pk.buf.data_ptr(), arr, L.stream_ptr(pk.device)), "rvq_search_stats")
-    return {"searched": int(arr[0]), "certified": int(arr[1]), "rescored": int(arr[2]), "fullscan": int(arr[3])}
+    names = ("searched", "certified", "rescored", "fullscan", "cyc_wait", "cyc_scores", "cyc_winner", "cyc_update",
+             "cyc_load", "cyc_total", "warps")
+    return {n: int(arr[i]) for i, n in enumerate(names)}

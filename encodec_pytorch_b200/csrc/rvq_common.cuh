@@ -28,12 +28,15 @@ constexpr int kTcKPad       = 144;                 // 128 dims + 16 augmented K 
 constexpr int kTcChunkBytes = kTcChunkCodes * kTcKPad * 2;  // 36864
 
 struct StageMeta {
-  float margin_coef;   // delta = margin_coef * (|x| + eps1): two-sided bound on the fp16 score error
+  // Two-sided bound on the fp16 tensor-core score error of a frame with norm |x| against any live
+  // code:  |S_k - s_k| <= delta/2,  delta = margin_coef * (|x| + eps1) + margin_abs.
+  float margin_coef;
+  float margin_abs;
   float xlimit;        // frames with |x| >= xlimit take the exact path (outlier codes / fp16 range)
   float cref;          // largest norm among non-outlier codes
   float cmin;          // smallest code norm
   int   n_outliers;    // codes excluded from the fp16 image (provably non-winning under xlimit)
-  int   reserved[3];
+  int   reserved[2];
 };
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }

@@ -41,7 +41,9 @@ __global__ void pack_copy_kernel(PtrTable32 src, unsigned char* pack, int stage_
 }
 
 // one block per stage: |c|^2, norm statistics, margin metadata and the fp16 UMMA image
-constexpr float kBetaFp16   = 4.1f * 4.8828125e-4f;  // 4.1 * 2^-11: |score error| <= beta*|x|*|c| (fp16 operands)
+// |score error| <= beta*|x|*|c|: fp16 rounding of x and of -2c (2 * 2^-11 * 2|x||c| by Cauchy-Schwarz)
+// plus slack (x1.125) for the tensor core's fp32 accumulation of 144 products
+constexpr float kBetaFp16   = 4.5f * 4.8828125e-4f;
 constexpr float kEps1       = 1e-3f;                 // absolute slack for fp16 subnormals
 constexpr float kOutlierMul = 64.f;                  // codes with |c| > 64 * median are outliers
 constexpr float kBigScore   = 60000.f;               // fp16-representable score of an outlier code
@@ -114,8 +116,10 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   if (threadIdx.x == 0) {
     StageMeta m;
     m.cref = s_cref; m.cmin = s_cmin; m.n_outliers = s_nout;
-    m.reserved[0] = m.reserved[1] = m.reserved[2] = 0;
+    m.reserved[0] = m.reserved[1] = 0;
     m.margin_coef = 2.f * kBetaFp16 * (s_cref + kEps1);
+    // |c|^2 is carried as fp16 hi + fp16 lo: error <= 2^-22 |c|^2 (+ 2^-24 when lo is subnormal)
+    m.margin_abs = 2.f * (2.4e-7f * s_cref * s_cref + 6e-8f);
     // |x| bound under which (a) outlier codes provably lose to the smallest-norm code and
     // (b) every live score + margin stays below the outlier score, (c) x fits fp16.
     float xl = 6.0e4f;
@@ -368,7 +372,7 @@ int simt_encode(const EncodeArgs& a, cudaStream_t st) {
 // ================================================================================================
 // chain kernels: one warp per frame walks the stages (decode / EMA statistics / residual combine)
 // ================================================================================================
-enum ChainMode { kDecode = 0, kStats = 1, kCombine = 2 };
+enum ChainMode { kDecode = 0, kStats = 1, kCombine = 2, kQuantSum = 3 };
 
 __device__ __forceinline__ void red_add_f4(float* addr, float4 v) {
 #if __CUDA_ARCH__ >= 900
@@ -384,7 +388,7 @@ chain_kernel(const unsigned char* pack, int K, int D,
              const float* __restrict__ x, FrameAddr fa, int64_t N, int stage0, int n_q,
              const int64_t* __restrict__ codes, int64_t scq, int64_t scb, int64_t sct, int T,
              const float* __restrict__ w, float* __restrict__ out,
-             float* __restrict__ counts, float* __restrict__ embed_sum, int ste) {
+             float* __restrict__ counts, float* __restrict__ embed_sum, int ste, int accum = 0) {
   PackView pv(pack, K, D);
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -396,7 +400,8 @@ chain_kernel(const unsigned char* pack, int K, int D,
       const int g = g0 + lane;
       const bool act = g < nd4;
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f), acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (MODE != kDecode && act) {
+      if (MODE == kQuantSum && accum && act) acc = *reinterpret_cast<const float4*>(out + n * D + g * 4);
+      if (MODE != kDecode && (MODE != kQuantSum || ste) && act) {
         const int64_t xb = fa.base(n) + int64_t(g) * 4 * fa.sxd;
         r.x = x[xb]; r.y = x[xb + fa.sxd]; r.z = x[xb + 2 * fa.sxd]; r.w = x[xb + 3 * fa.sxd];
       }
@@ -415,6 +420,13 @@ chain_kernel(const unsigned char* pack, int K, int D,
           if (!act) continue;
           float4 q = *reinterpret_cast<const float4*>(pv.tab32(s) + size_t(idx) * D + g * 4);
           if (MODE == kDecode) {
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+          } else if (MODE == kQuantSum) {
+            // running sum of the per-stage outputs (core_vq.py:349), straight-through values in training
+            if (ste) {
+              q.x = r.x + (q.x - r.x); q.y = r.y + (q.y - r.y); q.z = r.z + (q.z - r.z); q.w = r.w + (q.w - r.w);
+              r.x -= q.x; r.y -= q.y; r.z -= q.z; r.w -= q.w;
+            }
             acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
           } else {
             if (MODE == kStats) red_add_f4(embed_sum + (size_t(s0 + i) * K + idx) * D + g * 4, r);
@@ -438,6 +450,16 @@ static unsigned chain_grid(int64_t N) {
   const int64_t cap = 148 * 16;              // persistent-ish: a few waves over 148 SMs
   if (blocks > cap) blocks = cap;
   return unsigned(blocks < 1 ? 1 : blocks);
+}
+
+// quantized [N, D] = (accum ? quantized : 0) + sum over stages of the gathered rows (or of the
+// straight-through values), in stage order; companion launch of the tensor-core search
+int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa, int64_t N, int T, int stage0, int n_q,
+                   const int64_t* codes, float* out, int ste, int accum, cudaStream_t st) {
+  chain_kernel<kQuantSum><<<chain_grid(N), 256, 0, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0, n_q, codes,
+                                                        N, T, 1, T, nullptr, out, nullptr, nullptr, ste, accum);
+  RVQ_LAUNCH_CHECK("chain_kernel<quant_sum>");
+  return RVQ_OK;
 }
 
 }  // namespace rvq

@@ -185,9 +185,10 @@ def test_training_forward_ema_and_grad(golden_dir, case):
         st = assert_codes_match(pre, x, res.codes, g[f"s{s}_codes"])
         assert res.penalty.item() == pytest.approx(float(g[f"s{s}_penalty"]), rel=1e-5)
         exact = st["mismatch"] == 0
-        tol = dict(rtol=1e-5, atol=1e-6) if exact else dict(rtol=1e-2, atol=1e-2)
+        # 1e-5 relative to the tensor's scale (|values| reach ~10 after the first EMA steps)
+        tol = dict(rtol=1e-5, atol=2e-5) if exact else dict(rtol=1e-2, atol=1e-2)
         check_summary(res.quantized, g, f"s{s}_quantized", **tol)
-        check_summary(xg.grad, g, f"s{s}_grad", **(dict(rtol=1e-5, atol=1e-7) if exact else tol))
+        check_summary(xg.grad, g, f"s{s}_grad", **(dict(rtol=1e-5, atol=1e-6) if exact else tol))
         assert res.quantized.shape == xg.shape and res.codes.shape[1:] == (case.b, case.t)
         if not exact:
             pytest.skip("a documented near-tie moved a code; EMA state no longer comparable to the fixture")
