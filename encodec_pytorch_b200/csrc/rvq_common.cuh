@@ -18,14 +18,19 @@ namespace rvq {
 //     tab32   fp32 [K][D]    row-major copy of embed             (gathers, exact re-score)
 //     tab32T  fp32 [D][K]    transposed copy                     (exact SIMT search tiles)
 //     cnorm   fp32 [K]       |c_k|^2
-//     tc      fp16 image     (only D==128 && K%128==0) K/128 chunks of 36864 B, each the
-//                            shared-memory image of a 128-code x 144-K UMMA B operand
+//     tc      fp16 image     (only D==128 && K%64==0) K/64 chunks of 18432 B, each the
+//                            shared-memory image of a 64-code x 144-K UMMA B operand
 //     meta    StageMeta
 // ----------------------------------------------------------------------------------------------
 constexpr int kHeaderBytes  = 256;
-constexpr int kTcChunkCodes = 128;                 // codes per UMMA N tile
+constexpr int kTcChunkCodes = 64;                  // codes per UMMA N tile
 constexpr int kTcKPad       = 144;                 // 128 dims + 16 augmented K columns
-constexpr int kTcChunkBytes = kTcChunkCodes * kTcKPad * 2;  // 36864
+constexpr int kTcChunkBytes = kTcChunkCodes * kTcKPad * 2;  // 18432
+// image of chunk c: 18 K-groups (8 halves = 16 B each) x 64 code rows; element (row r, group g) at
+//   c*18432 + g*1024 + r*16  -> K-major, no swizzle: core matrix = 8 rows x 16 B contiguous,
+//   LBO (K direction) = 1024 B, SBO (row direction) = 128 B
+constexpr int kTcLBO = kTcChunkCodes * 16;         // 1024
+constexpr int kTcSBO = 128;
 
 struct StageMeta {
   // Two-sided bound on the fp16 tensor-core score error of a frame with norm |x| against any live
@@ -40,7 +45,7 @@ struct StageMeta {
 };
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
-__host__ __device__ inline bool tc_shape(int K, int D) { return D == 128 && K >= 128 && (K % kTcChunkCodes) == 0; }
+__host__ __device__ inline bool tc_shape(int K, int D) { return D == 128 && K >= 64 && K <= 1024 && (K % kTcChunkCodes) == 0; }
 
 struct StageLayout {
   size_t off_tab32, off_tab32T, off_cnorm, off_tc, off_meta, stride;

@@ -132,8 +132,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     m.xlimit = xl > 0.f ? xl : 0.f;
     *const_cast<StageMeta*>(pv.meta(s)) = m;
   }
-  // fp16 image: chunk c (128 codes) = 18 K-groups of 8 halves; element (row r, group g) at
-  //   c*36864 + g*2048 + r*16   (K-major, no swizzle: core matrix = 8 rows x 16 B contiguous)
+  // fp16 image (layout in rvq_common.cuh): chunk c = 64 codes x 18 K-groups of 8 halves
   unsigned char* img = const_cast<unsigned char*>(pv.tc(s));
   const int ngroups = kTcKPad / 8;   // 18
   for (int i = threadIdx.x; i < K * ngroups; i += blockDim.x) {
@@ -156,7 +155,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(0.f);
     }
-    *reinterpret_cast<uint4*>(img + size_t(c) * kTcChunkBytes + size_t(g) * 2048 + size_t(r) * 16) =
+    *reinterpret_cast<uint4*>(img + size_t(c) * kTcChunkBytes + size_t(g) * kTcLBO + size_t(r) * 16) =
         *reinterpret_cast<const uint4*>(h);
   }
 }

@@ -1,24 +1,29 @@
 // Fused multi-stage nearest-code search on the 5th-generation tensor cores (tcgen05 / TMEM).
 //
-// One persistent CTA per SM walks 128-frame tiles.  Per tile the fp32 residual of every frame
-// stays in shared memory across all n_q stages (core_vq.py:357-367 without the per-stage round
-// trips); per stage the scores  S[f,k] = -2 r_f . c_k + |c_k|^2  of all K codes are produced by
-// tcgen05.mma (fp16 operands, fp32 accumulate in TMEM) from
-//   A = fp16(r)  [128 frames x 144]  written by the frame threads (cols 128,129 = 1.0),
-//   B = fp16 image of the stage's codebook [128 codes x 144] per chunk (cols 0..127 = -2c,
-//       cols 128,129 = hi/lo halves of |c|^2), streamed by the TMA engine (cp.async.bulk) from the
-//       pre-arranged pack into a 3-slot ring.
-// The 128 frame threads (thread = TMEM lane = frame) read the scores back with tcgen05.ld and
-// keep, per frame, the minimum over each 32-code batch and over each residue class (code mod 32).
-// A code is within `delta` of the minimum iff its batch AND its class are; delta bounds the fp16
-// score error two-sidedly, so the exact fp32 winner is certified when one batch and one class
-// qualify, and otherwise the (at most four) candidates are re-scored with the reference's fp32
-// formula (core_vq.py:181-189, ties -> lowest index).  Anything else (fp16-range outliers, wide
-// ties) falls back to an exact fp32 scan of the whole table for that frame.  The winner's fp32
-// row is gathered, the residual updated exactly (core_vq.py:364 / :348 with the straight-through
-// arithmetic of :309 in training), and the new fp16 A operand written for the next stage.
+// One persistent CTA per SM owns a contiguous range of 128-frame tiles and walks it two tiles at
+// a time ("round"); both tiles of a round consume the SAME codebook chunk stream, so each chunk
+// is fetched from L2 once per 256 frames.  Per tile the fp32 residual of every frame stays in
+// shared memory across all n_q stages (core_vq.py:357-367 without the per-stage round trips);
+// per stage the scores  S[f,k] = -2 r_f . c_k + |c_k|^2  of all K codes come from tcgen05.mma
+// (fp16 operands, fp32 accumulation in TMEM):
+//   A = fp16(r) [128 frames x 144], kept in TENSOR MEMORY (written with tcgen05.st by the frame
+//       threads; columns 128,129 = 1.0 pick up the two halves of |c|^2),
+//   B = fp16 image of the codebook, 64 codes x 144 per chunk (cols 0..127 = -2c, cols 128,129 =
+//       hi/lo halves of |c|^2), streamed by the TMA engine (cp.async.bulk) from the pre-arranged
+//       pack into a shared-memory ring.
+// Each tile has 128 frame threads (thread = TMEM lane = frame).  They read the scores back with
+// tcgen05.ld and keep, per frame, the minimum over every 32-code batch and over every residue
+// class (code mod 32).  A code is within `delta` of the minimum iff its batch AND its class are;
+// delta bounds the fp16 score error two-sidedly (rvq_common.cuh, StageMeta), so the exact fp32
+// winner is certified when exactly one batch and one class qualify.  Otherwise the candidates
+// (flagged batches x flagged classes, usually 2..4 codes) are re-scored in fp32 with the
+// reference's formula (core_vq.py:181-189, ties -> lowest index), warp-cooperatively.  Frames
+// outside the fp16 image's validity range fall back to an exact fp32 scan of the table.  Then the
+// winner's fp32 row is gathered, the residual updated exactly (core_vq.py:364 / :348, with the
+// straight-through arithmetic of :309 in training) and the fp16 operand of the next stage written.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = frame threads.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = frames of tile slot 0,
+// 6..9 = frames of tile slot 1.
 #include "rvq_common.cuh"
 #include "rvq_ptx.cuh"
 
@@ -27,25 +32,26 @@ namespace rvq {
 namespace {
 
 constexpr int kM = 128;                 // frames per tile (UMMA M, TMEM lanes)
-constexpr int kNChunk = kTcChunkCodes;  // 128 codes per MMA group (UMMA N)
+constexpr int kN = kTcChunkCodes;       // 64 codes per MMA group (UMMA N)
 constexpr int kRing = 3;                // B ring slots
-constexpr int kAcc = 4;                 // TMEM accumulator buffers of 128 columns
 constexpr int kKSteps = kTcKPad / 16;   // 9 UMMA K steps of 16
-constexpr int kThreadsTc = 192;
+constexpr int kGroups = 2;              // tile slots per CTA
+constexpr int kThreadsTc = 64 + kGroups * 128;
 constexpr int kMaxBatches = 32;         // K <= 1024 on this path
-constexpr uint32_t kABytes = kM * kTcKPad * 2;   // 36864
-constexpr uint32_t kLBO = 2048, kSBO = 128;       // see rvq_common.cuh (pack image layout)
+constexpr int kListMax = 64;            // re-score entries per warp and stage handled cooperatively
+// TMEM columns of tile slot g: [g*256, +64) and [+64, +128) score buffers, [+128, +200) fp16 A operand
+constexpr uint32_t kTmemSlot = 256, kTmemA = 128;
 
 struct SmemLayout {
-  static constexpr uint32_t a = 0;
-  static constexpr uint32_t b = a + kABytes;
-  static constexpr uint32_t rs = b + kRing * kTcChunkBytes;          // fp32 residual [128 d][128 f]
-  static constexpr uint32_t bmin = rs + 128 * kM * 4;                // fp32 batch minima [32][128 f]
-  static constexpr uint32_t bars = bmin + kMaxBatches * kM * 4;
+  static constexpr uint32_t b = 0;                                         // ring of codebook chunks
+  static constexpr uint32_t rs = b + kRing * kTcChunkBytes;                // fp32 residual [g][128 d][128 f] (swizzled)
+  static constexpr uint32_t bmin = rs + kGroups * 128 * kM * 4;            // fp32 batch minima [g][32][128 f]
+  static constexpr uint32_t list = bmin + kGroups * kMaxBatches * kM * 4;  // re-score lists [8 warps][64]
+  static constexpr uint32_t bars = list + kGroups * 4 * kListMax * 4;
   static constexpr uint32_t total = bars + 256;
 };
 struct Bars {
-  uint64_t full[kRing], empty[kRing], acc_full[kAcc], acc_empty[kAcc], a_ready;
+  uint64_t full[kRing], empty[kRing], acc_full[kGroups][2], acc_empty[kGroups][2], a_ready[kGroups];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
@@ -61,6 +67,26 @@ struct TcParams {
 };
 
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
+// residual element (dim d, frame f) with an XOR swizzle: conflict-free both for "thread = frame,
+// fixed d" and for "fixed frame, lane = dim/4" (the cooperative re-score)
+__device__ __forceinline__ int rs_idx(int d, int f) { return d * kM + (f ^ ((d >> 2) & 31)); }
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+  #pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// tiles [start, start+cnt) of this CTA
+__device__ __forceinline__ void cta_range(int64_t ntiles, int64_t& start, int64_t& cnt) {
+  const int64_t base = ntiles / gridDim.x, rem = ntiles % gridDim.x;
+  const int64_t b = blockIdx.x;
+  start = b * base + (b < rem ? b : rem);
+  cnt = base + (b < rem ? 1 : 0);
+}
 
 }  // namespace
 
@@ -68,18 +94,21 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
   Bars* bars = reinterpret_cast<Bars*>(smem + SmemLayout::bars);
-  float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
-  float* sbmin = reinterpret_cast<float*>(smem + SmemLayout::bmin);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = 128;
   PackView pv(p.pack, p.K, D);
-  const int nchunks = p.K / kNChunk;
+  const int nchunks = p.K / kN;
   const int64_t ntiles = (p.N + kM - 1) / kM;
+  int64_t tile0, tcnt;
+  cta_range(ntiles, tile0, tcnt);
+  const int rounds = int((tcnt + kGroups - 1) / kGroups);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1); }
-    for (int i = 0; i < kAcc; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4); }
-    ptx::mbar_init(ptx::smem_u32(&bars->a_ready), kM);
+    for (int g = 0; g < kGroups; ++g) {
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->acc_full[g][i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[g][i]), 4); }
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[g]), kM);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -92,10 +121,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
-    // ===== TMA producer: the same chunk sequence (stage-major) for every tile of this CTA =====
+    // ===== TMA producer: one chunk stream (stage-major) per round, shared by both tile slots =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int r = 0; r < rounds; ++r) {
         for (int s = 0; s < p.n_q; ++s) {
           const unsigned char* img = pv.tc(p.stage0 + s);
           for (int c = 0; c < nchunks; ++c, ++it) {
@@ -112,52 +141,60 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kNChunk);
-      uint32_t it = 0, ait = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
+      uint32_t it = 0, ait = 0, acc_it[kGroups] = {0, 0};
+      for (int r = 0; r < rounds; ++r) {
+        const bool act1 = int64_t(r) * kGroups + 1 < tcnt;       // slot 1 idle in an odd last round
         for (int s = 0; s < p.n_q; ++s, ++ait) {
-          ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), ait & 1);          // fp16 residual operand written
-          ptx::tc_fence_after();
           for (int c = 0; c < nchunks; ++c, ++it) {
             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-            const uint32_t buf = it % kAcc, aph = (it / kAcc) & 1;
-            ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), aph ^ 1);   // epilogue drained this accumulator
-            ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), ph);            // codebook chunk landed
-            ptx::tc_fence_after();
-            const uint32_t a_addr = sbase + SmemLayout::a;
+            ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), ph);                 // codebook chunk landed
             const uint32_t b_addr = sbase + SmemLayout::b + slot * kTcChunkBytes;
             #pragma unroll
-            for (int k = 0; k < kKSteps; ++k) {
-              const uint64_t ad = ptx::umma_desc_kmajor_noswz(a_addr + k * 2 * kLBO, kLBO, kSBO);
-              const uint64_t bd = ptx::umma_desc_kmajor_noswz(b_addr + k * 2 * kLBO, kLBO, kSBO);
-              ptx::umma_f16_ss(tmem + buf * kNChunk, ad, bd, idesc, k > 0 ? 1u : 0u);
+            for (int g = 0; g < kGroups; ++g) {
+              if (g == 1 && !act1) continue;
+              if (c == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[g]), ait & 1);   // fp16 residual operand in TMEM
+              const uint32_t buf = acc_it[g] & 1, aph = (acc_it[g] >> 1) & 1;
+              ++acc_it[g];
+              ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[g][buf]), aph ^ 1);   // frame threads drained this buffer
+              ptx::tc_fence_after();
+              const uint32_t d_tmem = tmem + g * kTmemSlot + buf * kN;
+              const uint32_t a_tmem = tmem + g * kTmemSlot + kTmemA;
+              #pragma unroll
+              for (int k = 0; k < kKSteps; ++k) {
+                const uint64_t bd = ptx::umma_desc_kmajor_noswz(b_addr + k * 2 * kTcLBO, kTcLBO, kTcSBO);
+                ptx::umma_f16_ts(d_tmem, a_tmem + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+              }
+              ptx::umma_commit(ptx::smem_u32(&bars->acc_full[g][buf]));   // scores ready for the frame threads
             }
-            ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));       // ring slot reusable once the MMAs have read it
-            ptx::umma_commit(ptx::smem_u32(&bars->acc_full[buf]));     // scores ready for the frame threads
+            ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));          // ring slot reusable once read
           }
         }
       }
     }
     __syncwarp();
   } else {
-    // ===== frame threads: thread <-> TMEM lane <-> frame of the tile =====
-    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int f = q * 32 + lane;               // frame row within the tile
-    const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);
-    unsigned char* arow = smem + SmemLayout::a + f * 16;
-    // augmented K columns never change: col 128,129 = 1 (pick up hi/lo of |c|^2), rest 0
+    // ===== frame threads: thread <-> TMEM lane <-> frame of the slot's tile =====
+    const int g = (warp - 2) >> 2;             // tile slot
+    const int wq = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int f = wq * 32 + lane;              // frame row within the tile
+    const uint32_t tlane = tmem + g * kTmemSlot + (uint32_t(wq * 32) << 16);
+    float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs) + g * 128 * kM;
+    float* sbmin = reinterpret_cast<float*>(smem + SmemLayout::bmin) + g * kMaxBatches * kM;
+    uint32_t* wlist = reinterpret_cast<uint32_t*>(smem + SmemLayout::list) + (warp - 2) * kListMax;
+    const uint32_t bar_a = ptx::smem_u32(&bars->a_ready[g]);
+    // augmented K columns never change: cols 128,129 = 1 (pick up hi/lo of |c|^2), rest 0
     {
-      __align__(16) __half h[8];
-      #pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(j < 2 ? 1.f : 0.f);
-      *reinterpret_cast<uint4*>(arow + 16 * kLBO) = *reinterpret_cast<const uint4*>(h);
-      *reinterpret_cast<uint4*>(arow + 17 * kLBO) = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t w8[8] = {pack_half2(1.f, 1.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      ptx::tmem_st8(tlane + kTmemA + 64, w8);
     }
     unsigned long long n_cert = 0, n_resc = 0, n_full = 0, n_all = 0;
     long long t_wait = 0, t_epi = 0, t_win = 0, t_upd = 0, t_load = 0;   // phase cycles (lane 0 of each warp)
     const long long t_begin = clock64();
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint32_t acc_it = 0;
+    for (int r = 0; r < rounds; ++r) {
+      if (int64_t(r) * kGroups + g >= tcnt) break;     // idle slot in the last round
+      const int64_t tile = tile0 + int64_t(r) * kGroups + g;
       const int64_t n = tile * kM + f;
       const bool valid = n < p.N;
       long long tc0 = clock64();
@@ -166,23 +203,27 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       {
         const int64_t xb = valid ? p.fa.base(n) : 0;
         float part[4] = {0.f, 0.f, 0.f, 0.f};
-        #pragma unroll 4
-        for (int g = 0; g < 16; ++g) {
-          __align__(16) __half h[8];
+        #pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float v[32];
           #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int d = g * 8 + j;
-            const float v = valid ? __ldg(p.x + xb + int64_t(d) * p.fa.sxd) : 0.f;
-            rs[d * kM + f] = v;
-            part[g >> 2] = fmaf(v, v, part[g >> 2]);
-            h[j] = __float2half_rn(v);
+          for (int j = 0; j < 32; ++j) v[j] = valid ? __ldg(p.x + xb + int64_t(h * 32 + j) * p.fa.sxd) : 0.f;
+          #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            rs[rs_idx(h * 32 + j, f)] = v[j];
+            part[h] = fmaf(v[j], v[j], part[h]);
           }
-          *reinterpret_cast<uint4*>(arow + g * kLBO) = *reinterpret_cast<const uint4*>(h);
+          uint32_t w0[8], w1[8];
+          #pragma unroll
+          for (int j = 0; j < 8; ++j) { w0[j] = pack_half2(v[2 * j], v[2 * j + 1]); w1[j] = pack_half2(v[16 + 2 * j], v[17 + 2 * j]); }
+          ptx::tmem_st8(tlane + kTmemA + h * 16, w0);
+          ptx::tmem_st8(tlane + kTmemA + h * 16 + 8, w1);
         }
         xx = ((part[0] + part[1]) + part[2]) + part[3];
       }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_a);
       { const long long t = clock64(); t_load += t - tc0; tc0 = t; }
 
       for (int s = 0; s < p.n_q; ++s) {
@@ -195,17 +236,20 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         #pragma unroll
         for (int j = 0; j < 32; ++j) cm[j] = inf_f();
 
-        for (int c = 0; c < nchunks; ++c, ++it) {
-          const uint32_t buf = it % kAcc, aph = (it / kAcc) & 1;
-          ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), aph);
+        for (int c = 0; c < nchunks; ++c, ++acc_it) {
+          const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+          ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[g][buf]), aph);
           ptx::tc_fence_after();
           { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
-          #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          {
             uint32_t v0[32], v1[32];
-            ptx::tmem_ld32(tlane + buf * kNChunk + half * 64, v0);
-            ptx::tmem_ld32(tlane + buf * kNChunk + half * 64 + 32, v1);
+            ptx::tmem_ld32(tlane + buf * kN, v0);
+            ptx::tmem_ld32(tlane + buf * kN + 32, v1);
             ptx::tmem_ld_wait();
+            // scores are in registers: hand the accumulator back before reducing them
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[g][buf]));
             #pragma unroll
             for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
             float t0[11], t1[11];
@@ -220,66 +264,83 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
             float b1 = ptx::fmin3(ptx::fmin3(t1[0], t1[1], t1[2]), ptx::fmin3(t1[3], t1[4], t1[5]), ptx::fmin3(t1[6], t1[7], t1[8]));
             b0 = ptx::fmin3(b0, t0[9], t0[10]);
             b1 = ptx::fmin3(b1, t1[9], t1[10]);
-            sbmin[(c * 4 + half * 2) * kM + f] = b0;
-            sbmin[(c * 4 + half * 2 + 1) * kM + f] = b1;
+            sbmin[(c * 2) * kM + f] = b0;
+            sbmin[(c * 2 + 1) * kM + f] = b1;
           }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));
           { const long long t = clock64(); t_epi += t - tc0; tc0 = t; }
         }
 
         // ---- winner: certified / re-scored / exact scan ----
         float m = inf_f();
         #pragma unroll
-        for (int j = 0; j < 32; ++j) m = fminf(m, cm[j]);
+        for (int j = 0; j < 32; j += 2) m = ptx::fmin3(m, cm[j], cm[j + 1]);
         const float thr = m + delta;
         uint32_t cmask = 0, bmask = 0;
         #pragma unroll
         for (int j = 0; j < 32; ++j) cmask |= (cm[j] <= thr) ? (1u << j) : 0u;
-        const int nb = nchunks * 4;
+        const int nb = nchunks * 2;
         for (int a = 0; a < nb; ++a) bmask |= (sbmin[a * kM + f] <= thr) ? (1u << a) : 0u;
         const int ncl = __popc(cmask), nba = __popc(bmask);
         const float* t32 = pv.tab32(st);
         const float* cn = pv.cnorm(st);
         int idx = 0;
-        const bool need_full = outl || cmask == 0u || bmask == 0u;       // masks are empty only for NaN scores
-        if (!need_full) {
-          if (ncl == 1 && nba == 1) {
-            idx = (__ffs(bmask) - 1) * 32 + (__ffs(cmask) - 1);
-            ++n_cert;
+        bool need_full = outl || cmask == 0u || bmask == 0u;       // masks are empty only for NaN scores
+        const bool certified = !need_full && ncl == 1 && nba == 1;
+        if (certified) { idx = (__ffs(bmask) - 1) * 32 + (__ffs(cmask) - 1); ++n_cert; }
+        const bool need_resc = !need_full && !certified;
+        const uint32_t resc_mask = __ballot_sync(0xffffffffu, need_resc);
+        if (resc_mask != 0u) {
+          // candidates = flagged batches x flagged classes.  All lanes' candidates go to one list
+          // (ascending code order per frame) that the warp then scores cooperatively: lane l holds
+          // dims 4l..4l+3 of the code row (coalesced 512-B read) and of the frame's residual.
+          const int mine = need_resc ? ncl * nba : 0;
+          int pre = mine;
+          #pragma unroll
+          for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, pre, off); if (lane >= off) pre += o; }
+          const int total = __shfl_sync(0xffffffffu, pre, 31);
+          if (total > kListMax) {
+            if (need_resc) need_full = true;           // pathological tie width: exact scan instead
           } else {
-            // candidates = flagged batches x flagged classes, visited in ascending code order so that
-            // the strict '<' keeps the lowest index among exact ties (core_vq.py:188)
-            float best = inf_f(); int bi = 0x7fffffff;
-            uint32_t bm2 = bmask;
-            while (bm2) {
-              const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
-              uint32_t cm2 = cmask;
-              while (cm2) {
-                const int j = __ffs(cm2) - 1; cm2 &= cm2 - 1;
-                const int code = a * 32 + j;
-                const float4* row = reinterpret_cast<const float4*>(t32 + size_t(code) * D);
-                float acc = 0.f;
-                #pragma unroll 4
-                for (int d4 = 0; d4 < 32; ++d4) {
-                  const float4 cv = __ldg(row + d4);
-                  acc = fmaf(rs[(d4 * 4 + 0) * kM + f], cv.x, acc);
-                  acc = fmaf(rs[(d4 * 4 + 1) * kM + f], cv.y, acc);
-                  acc = fmaf(rs[(d4 * 4 + 2) * kM + f], cv.z, acc);
-                  acc = fmaf(rs[(d4 * 4 + 3) * kM + f], cv.w, acc);
-                }
-                const float dist = (xx - 2.f * acc) + __ldg(cn + code);     // core_vq.py:183-187
-                if (dist < best) { best = dist; bi = code; }
+            int pos = pre - mine;
+            if (need_resc) {
+              uint32_t bm2 = bmask;
+              while (bm2) {
+                const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
+                uint32_t cm2 = cmask;
+                while (cm2) { const int j = __ffs(cm2) - 1; cm2 &= cm2 - 1; wlist[pos++] = (uint32_t(lane) << 16) | uint32_t(a * 32 + j); }
               }
             }
-            idx = bi == 0x7fffffff ? 0 : bi;
-            ++n_resc;
+            __syncwarp();
+            float best = inf_f(); int bi = 0x7fffffff;
+            for (int e0 = 0; e0 < total; e0 += 4) {
+              float part[4], xxo[4]; int code[4], own[4];
+              #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t ent = wlist[min(e0 + u, total - 1)];
+                own[u] = int(ent >> 16); code[u] = int(ent & 0xffffu);
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(t32 + size_t(code[u]) * D) + lane);
+                const int fo = wq * 32 + own[u];
+                float acc = rs[rs_idx(4 * lane + 0, fo)] * cv.x;
+                acc = fmaf(rs[rs_idx(4 * lane + 1, fo)], cv.y, acc);
+                acc = fmaf(rs[rs_idx(4 * lane + 2, fo)], cv.z, acc);
+                acc = fmaf(rs[rs_idx(4 * lane + 3, fo)], cv.w, acc);
+                part[u] = acc;
+                xxo[u] = __shfl_sync(0xffffffffu, xx, own[u]);
+              }
+              #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float dot = warp_sum(part[u]);
+                const float dist = (xxo[u] - 2.f * dot) + __ldg(cn + code[u]);      // core_vq.py:183-187
+                if (e0 + u < total && lane == own[u] && dist < best) { best = dist; bi = code[u]; }
+              }
+            }
+            if (need_resc) { idx = bi == 0x7fffffff ? 0 : bi; ++n_resc; }
+            __syncwarp();
           }
         }
         if (__any_sync(0xffffffffu, need_full)) {
-          // frames outside the fp16 image's validity range (or NaN): exact fp32 scan of the whole
-          // table, all lanes in lockstep (code rows are warp-uniform loads)
+          // frames outside the fp16 image's validity range, NaN, or absurd tie widths: exact fp32
+          // scan of the whole table, all lanes in lockstep (code rows are warp-uniform loads)
           float best = inf_f(); int bi = 0x7fffffff;
           for (int k = 0; k < p.K; ++k) {
             const float4* row = reinterpret_cast<const float4*>(t32 + size_t(k) * D);
@@ -287,10 +348,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
             #pragma unroll 4
             for (int d4 = 0; d4 < 32; ++d4) {
               const float4 cv = __ldg(row + d4);
-              acc = fmaf(rs[(d4 * 4 + 0) * kM + f], cv.x, acc);
-              acc = fmaf(rs[(d4 * 4 + 1) * kM + f], cv.y, acc);
-              acc = fmaf(rs[(d4 * 4 + 2) * kM + f], cv.z, acc);
-              acc = fmaf(rs[(d4 * 4 + 3) * kM + f], cv.w, acc);
+              acc = fmaf(rs[rs_idx(d4 * 4 + 0, f)], cv.x, acc);
+              acc = fmaf(rs[rs_idx(d4 * 4 + 1, f)], cv.y, acc);
+              acc = fmaf(rs[rs_idx(d4 * 4 + 2, f)], cv.z, acc);
+              acc = fmaf(rs[rs_idx(d4 * 4 + 3, f)], cv.w, acc);
             }
             const float dist = (xx - 2.f * acc) + __ldg(cn + k);
             if (dist < best) { best = dist; bi = k; }
@@ -304,33 +365,40 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         {
           const float4* row = reinterpret_cast<const float4*>(t32 + size_t(idx) * D);
           float part[4] = {0.f, 0.f, 0.f, 0.f};
-          #pragma unroll 4
-          for (int g = 0; g < 16; ++g) {
-            const float4 c0 = __ldg(row + 2 * g), c1 = __ldg(row + 2 * g + 1);
-            const float cq[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            __align__(16) __half h[8];
+          #pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float4 cq[8];
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) cq[j] = __ldg(row + h * 8 + j);
+            uint32_t w0[8], w1[8];
             #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int d = g * 8 + j;
-              const float r = rs[d * kM + f];
-              float qv = cq[j];
-              if (p.ste) qv = r + (qv - r);                 // core_vq.py:309
-              const float rn = r - qv;                       // core_vq.py:364 / :348
-              rs[d * kM + f] = rn;
-              part[g >> 2] = fmaf(rn, rn, part[g >> 2]);
-              h[j] = __float2half_rn(rn);
+              const float cv[4] = {cq[j].x, cq[j].y, cq[j].z, cq[j].w};
+              float rn[4];
+              #pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int d = h * 32 + j * 4 + i;
+                const float rv = rs[rs_idx(d, f)];
+                float qv = cv[i];
+                if (p.ste) qv = rv + (qv - rv);               // core_vq.py:309
+                rn[i] = rv - qv;                               // core_vq.py:364 / :348
+                rs[rs_idx(d, f)] = rn[i];
+                part[h] = fmaf(rn[i], rn[i], part[h]);
+              }
+              if (j < 4) { w0[2 * j] = pack_half2(rn[0], rn[1]); w0[2 * j + 1] = pack_half2(rn[2], rn[3]); }
+              else       { w1[2 * (j - 4)] = pack_half2(rn[0], rn[1]); w1[2 * (j - 4) + 1] = pack_half2(rn[2], rn[3]); }
             }
-            *reinterpret_cast<uint4*>(arow + g * kLBO) = *reinterpret_cast<const uint4*>(h);
+            ptx::tmem_st8(tlane + kTmemA + h * 16, w0);
+            ptx::tmem_st8(tlane + kTmemA + h * 16 + 8, w1);
           }
           xx = ((part[0] + part[1]) + part[2]) + part[3];
         }
-        ptx::fence_proxy_async_smem();
-        if (s + 1 < p.n_q) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        if (s + 1 < p.n_q) ptx::mbar_arrive(bar_a);
         if (valid) p.codes[int64_t(s) * p.N + n] = idx;
         if (p.sqerr != nullptr) {
-          float v = valid ? xx : 0.f;
-          #pragma unroll
-          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          const float v = warp_sum(valid ? xx : 0.f);
           if (lane == 0) atomicAdd(&p.sqerr[s], (double)v);
         }
         { const long long t = clock64(); t_upd += t - tc0; tc0 = t; }
@@ -339,11 +407,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         float* out = p.residual_out + n * D;
         #pragma unroll 4
         for (int d4 = 0; d4 < 32; ++d4)
-          *reinterpret_cast<float4*>(out + d4 * 4) = make_float4(rs[(d4 * 4) * kM + f], rs[(d4 * 4 + 1) * kM + f],
-                                                                 rs[(d4 * 4 + 2) * kM + f], rs[(d4 * 4 + 3) * kM + f]);
+          *reinterpret_cast<float4*>(out + d4 * 4) = make_float4(rs[rs_idx(d4 * 4, f)], rs[rs_idx(d4 * 4 + 1, f)],
+                                                                 rs[rs_idx(d4 * 4 + 2, f)], rs[rs_idx(d4 * 4 + 3, f)]);
       }
     }
-    // search statistics (evidence for the certified / re-scored / exact-scan split)
+    // search statistics and phase cycles (evidence; see rvq_search_stats)
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       n_all += __shfl_xor_sync(0xffffffffu, n_all, off);
@@ -372,7 +440,7 @@ int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa,
 int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   const int64_t N = int64_t(a.B) * a.T;
   if (N == 0 || a.n_q == 0) return RVQ_OK;
-  RVQ_REQUIRE(a.D == 128 && a.K % kNChunk == 0 && a.K <= kMaxBatches * 32, "tc_encode: shape D=%d K=%d", a.D, a.K);
+  RVQ_REQUIRE(tc_shape(a.K, a.D), "tc_encode: shape D=%d K=%d", a.D, a.K);
   static thread_local int sm_count = 0, sm_dev = -1;
   int dev = 0;
   RVQ_CUDA(cudaGetDevice(&dev));
@@ -391,7 +459,8 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   p.ste = (a.flags & RVQ_FLAG_STE) ? 1 : 0;
   p.counters = pv.counters();
   const int64_t ntiles = (N + kM - 1) / kM;
-  const unsigned grid = unsigned(ntiles < sm_count ? ntiles : sm_count);
+  const int64_t pairs = (ntiles + kGroups - 1) / kGroups;
+  const unsigned grid = unsigned(pairs < sm_count ? pairs : sm_count);
   tc_encode_kernel<<<grid, kThreadsTc, SmemLayout::total, st>>>(p);
   RVQ_LAUNCH_CHECK("tc_encode_kernel");
   if (a.quantized != nullptr)
