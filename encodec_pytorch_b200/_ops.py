@@ -222,9 +222,9 @@ def residual_combine(pk: CodebookPack, x: torch.Tensor, codes: torch.Tensor, sta
 def search_stats(pk: CodebookPack) -> tp.Dict[str, int]:
     import ctypes as C
     lib = L.load()
-    arr = (C.c_uint64 * 16)()
+    arr = (C.c_uint64 * 32)()
     with _guard(pk.device):
         L.check(lib.rvq_search_stats(pk.buf.data_ptr(), arr, L.stream_ptr(pk.device)), "rvq_search_stats")
     names = ("searched", "certified", "rescored", "fullscan", "cyc_wait", "cyc_scores", "cyc_winner", "cyc_update",
-             "cyc_load", "cyc_total", "warps")
+             "cyc_load", "cyc_total", "warps", "mma_wait_a", "mma_wait_full", "mma_wait_acc", "mma_total", "cyc_resolve", "cyc_pairbar", "tma_late_lat_sum", "tma_late_n", "mma_issue")
     return {n: int(arr[i]) for i, n in enumerate(names)}

@@ -106,7 +106,7 @@ int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int6
 int rvq_search_stats(const void* pack, uint64_t* out_host, void* stream) {
   if (int e = check_device()) return e;
   RVQ_REQUIRE(pack && out_host, "rvq_search_stats: null pointer");
-  RVQ_CUDA(cudaMemcpyAsync(out_host, pack, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  RVQ_CUDA(cudaMemcpyAsync(out_host, pack, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   RVQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return RVQ_OK;
 }

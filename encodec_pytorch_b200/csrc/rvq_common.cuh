@@ -18,18 +18,18 @@ namespace rvq {
 //     tab32   fp32 [K][D]    row-major copy of embed             (gathers, exact re-score)
 //     tab32T  fp32 [D][K]    transposed copy                     (exact SIMT search tiles)
 //     cnorm   fp32 [K]       |c_k|^2
-//     tc      fp16 image     (only D==128 && K%64==0) K/64 chunks of 18432 B, each the
-//                            shared-memory image of a 64-code x 144-K UMMA B operand
+//     tc      fp16 image     (only D==128 && K%128==0) K/128 chunks of 36864 B, each the
+//                            shared-memory image of a 128-code x 144-K UMMA B operand
 //     meta    StageMeta
 // ----------------------------------------------------------------------------------------------
 constexpr int kHeaderBytes  = 256;
-constexpr int kTcChunkCodes = 64;                  // codes per UMMA N tile
+constexpr int kTcChunkCodes = 128;                 // codes per UMMA N tile
 constexpr int kTcKPad       = 144;                 // 128 dims + 16 augmented K columns
-constexpr int kTcChunkBytes = kTcChunkCodes * kTcKPad * 2;  // 18432
-// image of chunk c: 18 K-groups (8 halves = 16 B each) x 64 code rows; element (row r, group g) at
-//   c*18432 + g*1024 + r*16  -> K-major, no swizzle: core matrix = 8 rows x 16 B contiguous,
-//   LBO (K direction) = 1024 B, SBO (row direction) = 128 B
-constexpr int kTcLBO = kTcChunkCodes * 16;         // 1024
+constexpr int kTcChunkBytes = kTcChunkCodes * kTcKPad * 2;  // 36864
+// image of chunk c: 18 K-groups (8 halves = 16 B each) x 128 code rows; element (row r, group g) at
+//   c*36864 + g*2048 + r*16  -> K-major, no swizzle: core matrix = 8 rows x 16 B contiguous,
+//   LBO (K direction) = 2048 B, SBO (row direction) = 128 B
+constexpr int kTcLBO = kTcChunkCodes * 16;         // 2048
 constexpr int kTcSBO = 128;
 
 struct StageMeta {
@@ -41,11 +41,12 @@ struct StageMeta {
   float cref;          // largest norm among non-outlier codes
   float cmin;          // smallest code norm
   int   n_outliers;    // codes excluded from the fp16 image (provably non-winning under xlimit)
-  int   reserved[2];
+  float cmax_all;      // largest norm among ALL codes (bounds the residual growth of exact-path frames)
+  int   reserved;
 };
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
-__host__ __device__ inline bool tc_shape(int K, int D) { return D == 128 && K >= 64 && K <= 1024 && (K % kTcChunkCodes) == 0; }
+__host__ __device__ inline bool tc_shape(int K, int D) { return D == 128 && K >= kTcChunkCodes && K <= 1024 && (K % kTcChunkCodes) == 0; }
 
 struct StageLayout {
   size_t off_tab32, off_tab32T, off_cnorm, off_tc, off_meta, stride;

@@ -33,6 +33,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time before answering)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -72,6 +84,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t smem_addr, u
   d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= uint64_t(1) << 46;
+  return d;
+}
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 64 halves (128 B), 8-row groups of
+// 1024 B (SBO), 16-byte chunks XOR-swizzled with (row % 8); the tile base must be 1024-byte aligned.  A K=16
+// step inside the 128-byte row advances the start address by 32 B.  Layout type 2 = SWIZZLE_128B (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t(1) << 16;               // LBO: unused for swizzled K-major layouts
+  d |= uint64_t(1024 >> 4) << 32;       // SBO: 8 rows x 128 B
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16: D fp32 (bit 4), A/B fp16 (0), both K-major, N>>3 at [17,23),
@@ -134,6 +158,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- named barrier among a subset of the CTA's warps (ids 1..15; 0 is __syncthreads) ----------------------
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ---- 3-input float min (FMNMX3 on sm_100) ----------------------------------------------------------
 __device__ __forceinline__ float fmin3(float a, float b, float c) {

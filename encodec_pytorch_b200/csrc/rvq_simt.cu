@@ -90,12 +90,13 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       __syncthreads();
     }
   }
-  __shared__ float s_thr, s_cref, s_cmin, s_outmin;
+  __shared__ float s_thr, s_cref, s_cmin, s_outmin, s_cmax;
   __shared__ int s_nout;
   if (threadIdx.x == 0) {
     float med = norms[K / 2];
     s_thr = kOutlierMul * med;
     s_cmin = norms[0];
+    s_cmax = norms[K - 1];
     s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0;
   }
   __syncthreads();
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   if (threadIdx.x == 0) {
     StageMeta m;
     m.cref = s_cref; m.cmin = s_cmin; m.n_outliers = s_nout;
-    m.reserved[0] = m.reserved[1] = 0;
+    m.cmax_all = s_cmax; m.reserved = 0;
     m.margin_coef = 2.f * kBetaFp16 * (s_cref + kEps1);
     // |c|^2 is carried as fp16 hi + fp16 lo: error <= 2^-22 |c|^2 (+ 2^-24 when lo is subnormal)
     m.margin_abs = 2.f * (2.4e-7f * s_cref * s_cref + 6e-8f);
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     m.xlimit = xl > 0.f ? xl : 0.f;
     *const_cast<StageMeta*>(pv.meta(s)) = m;
   }
-  // fp16 image (layout in rvq_common.cuh): chunk c = 64 codes x 18 K-groups of 8 halves
+  // fp16 image (layout in rvq_common.cuh): chunk c = 128 codes x 18 K-groups of 8 halves
   unsigned char* img = const_cast<unsigned char*>(pv.tc(s));
   const int ngroups = kTcKPad / 8;   // 18
   for (int i = threadIdx.x; i < K * ngroups; i += blockDim.x) {

@@ -1,29 +1,28 @@
 // Fused multi-stage nearest-code search on the 5th-generation tensor cores (tcgen05 / TMEM).
 //
-// One persistent CTA per SM owns a contiguous range of 128-frame tiles and walks it two tiles at
-// a time ("round"); both tiles of a round consume the SAME codebook chunk stream, so each chunk
-// is fetched from L2 once per 256 frames.  Per tile the fp32 residual of every frame stays in
-// shared memory across all n_q stages (core_vq.py:357-367 without the per-stage round trips);
-// per stage the scores  S[f,k] = -2 r_f . c_k + |c_k|^2  of all K codes come from tcgen05.mma
-// (fp16 operands, fp32 accumulation in TMEM):
-//   A = fp16(r) [128 frames x 144], kept in TENSOR MEMORY (written with tcgen05.st by the frame
-//       threads; columns 128,129 = 1.0 pick up the two halves of |c|^2),
-//   B = fp16 image of the codebook, 64 codes x 144 per chunk (cols 0..127 = -2c, cols 128,129 =
-//       hi/lo halves of |c|^2), streamed by the TMA engine (cp.async.bulk) from the pre-arranged
-//       pack into a shared-memory ring.
-// Each tile has 128 frame threads (thread = TMEM lane = frame).  They read the scores back with
-// tcgen05.ld and keep, per frame, the minimum over every 32-code batch and over every residue
-// class (code mod 32).  A code is within `delta` of the minimum iff its batch AND its class are;
-// delta bounds the fp16 score error two-sidedly (rvq_common.cuh, StageMeta), so the exact fp32
-// winner is certified when exactly one batch and one class qualify.  Otherwise the candidates
-// (flagged batches x flagged classes, usually 2..4 codes) are re-scored in fp32 with the
-// reference's formula (core_vq.py:181-189, ties -> lowest index), warp-cooperatively.  Frames
-// outside the fp16 image's validity range fall back to an exact fp32 scan of the table.  Then the
-// winner's fp32 row is gathered, the residual updated exactly (core_vq.py:364 / :348, with the
-// straight-through arithmetic of :309 in training) and the fp16 operand of the next stage written.
-//
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = frames of tile slot 0,
-// 6..9 = frames of tile slot 1.
+// One persistent CTA per SM walks a contiguous range of 128-frame tiles.  The fp32 residual of every
+// frame of the tile stays in shared memory across all n_q stages (core_vq.py:357-367 without the
+// per-stage round trips through HBM).  Per stage the scores  S[f,k] = -2 r_f . c_k + |c_k|^2  of all K
+// codes come from tcgen05.mma (fp16 operands, fp32 accumulation in tensor memory), 128 codes per MMA
+// group (M=128, N=128, 9 K-steps of 16 -- the issue-rate floor measured by scripts/ubench_tc.cu):
+//   A = fp16(r) [128 frames x 144] in shared memory: two 128B-swizzled K-major blocks of 64 dims that
+//       the frame warps rewrite every stage, plus a constant block whose columns 128,129 = 1 pick up
+//       the hi/lo halves of |c|^2;
+//   B = fp16 image of the codebook, 128 codes x 144 per chunk (cols 0..127 = -2c, cols 128,129 = hi/lo
+//       of |c|^2), streamed by the TMA engine (cp.async.bulk) from the pre-arranged pack into a ring.
+// Warp roles (320 threads): 0..3 = score warps (thread = TMEM lane = frame), 4..7 = helper warps, 8 = TMA
+// producer, 9 = MMA issuer of the even chunks (+ TMEM alloc), 10 = MMA issuer of the odd chunks.  A score warp reads the accumulators with
+// tcgen05.ld and keeps, per frame, the minimum over every 32-code batch and over every residue class
+// (code mod 32).  A code is within `delta` of the minimum iff its batch AND its class are; delta bounds
+// the fp16 score error two-sidedly (rvq_common.cuh, StageMeta), so the exact fp32 winner is certified
+// when exactly one batch and one class qualify.  Otherwise the candidates (flagged batches x flagged
+// classes, usually 2..4 codes) are re-scored in fp32 with the reference's formula (core_vq.py:181-189,
+// ties -> lowest index).  Frames outside the fp16 image's validity range take an exact fp32 scan.
+// The update pass runs "lane = dimension": for each frame a half-warp reads the candidate rows of the
+// fp32 table (coalesced 512-byte rows, prefetched one frame ahead), re-scores if needed, updates the
+// residual exactly (core_vq.py:364 / :348, with the straight-through arithmetic of :309 in training)
+// and writes the fp16 operand of the next stage.  Score warp q and helper warp q split the 32 frames
+// of TMEM lane quadrant q for that pass.
 #include "rvq_common.cuh"
 #include "rvq_ptx.cuh"
 
@@ -32,30 +31,35 @@ namespace rvq {
 namespace {
 
 constexpr int kM = 128;                 // frames per tile (UMMA M, TMEM lanes)
-constexpr int kN = kTcChunkCodes;       // 64 codes per MMA group (UMMA N)
+constexpr int kN = kTcChunkCodes;       // 128 codes per MMA group (UMMA N)
 constexpr int kRing = 3;                // B ring slots
 constexpr int kKSteps = kTcKPad / 16;   // 9 UMMA K steps of 16
-constexpr int kGroups = 2;              // tile slots per CTA
-constexpr int kThreadsTc = 64 + kGroups * 128;
-constexpr int kMaxBatches = 32;         // K <= 1024 on this path
-constexpr int kListMax = 64;            // re-score entries per warp and stage handled cooperatively
-// TMEM columns of tile slot g: [g*256, +64) and [+64, +128) score buffers, [+128, +200) fp16 A operand
-constexpr uint32_t kTmemSlot = 256, kTmemA = 128;
+constexpr int kAccBufs = 4;             // accumulator buffers of kN TMEM columns
+constexpr int kMaxChunks = 8;           // K <= 1024 on this path
+constexpr int kThreadsTc = 96 + 8 * 32;   // 8 frame warps + TMA producer + 2 MMA issuers
+constexpr int kBig = 5;                 // ncnt marker: more than 4 candidates (enumerate the masks)
+constexpr int kFull = 6;                // ncnt marker: exact scan of the whole table
 
 struct SmemLayout {
-  static constexpr uint32_t b = 0;                                         // ring of codebook chunks
-  static constexpr uint32_t rs = b + kRing * kTcChunkBytes;                // fp32 residual [g][128 d][128 f] (swizzled)
-  static constexpr uint32_t bmin = rs + kGroups * 128 * kM * 4;            // fp32 batch minima [g][32][128 f]
-  static constexpr uint32_t list = bmin + kGroups * kMaxBatches * kM * 4;  // re-score lists [8 warps][64]
-  static constexpr uint32_t bars = list + kGroups * 4 * kListMax * 4;
+  static constexpr uint32_t a_sw = 0;                              // 2 x [128 rows][128 B], 128B swizzle
+  static constexpr uint32_t a_aug = a_sw + 2 * 16384;              // [2 k-groups][128 rows][16 B], no swizzle
+  static constexpr uint32_t b = a_aug + 4096;                      // ring of codebook chunks
+  static constexpr uint32_t rs = b + kRing * kTcChunkBytes;        // fp32 residual [128 f][128 d], chunk-swizzled
+  static constexpr uint32_t cand = rs + kM * 128 * 4;              // int4 [128]: candidate codes (-1 = none)
+  static constexpr uint32_t ncnt = cand + kM * 16;                 // int [128]
+  static constexpr uint32_t cmask = ncnt + kM * 4;                 // u32 [128] flagged classes
+  static constexpr uint32_t bmask = cmask + kM * 4;                // u32 [128] flagged batches
+  static constexpr uint32_t xpart = bmask + kM * 4;                // float [4][128] partial |x|^2
+  static constexpr uint32_t bars = xpart + 4 * kM * 4;
   static constexpr uint32_t total = bars + 256;
 };
 struct Bars {
-  uint64_t full[kRing], empty[kRing], acc_full[kGroups][2], acc_empty[kGroups][2], a_ready[kGroups];
+  uint64_t full[kRing], empty[kRing], acc_full[kAccBufs], acc_empty[kAccBufs], a_ready;
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 static_assert(SmemLayout::total <= 227 * 1024, "shared memory budget");
+static_assert(kKSteps == 9 && kN == 128, "operand geometry");
 
 struct TcParams {
   const unsigned char* pack; int K;
@@ -67,9 +71,11 @@ struct TcParams {
 };
 
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
-// residual element (dim d, frame f) with an XOR swizzle: conflict-free both for "thread = frame,
-// fixed d" and for "fixed frame, lane = dim/4" (the cooperative re-score)
-__device__ __forceinline__ int rs_idx(int d, int f) { return d * kM + (f ^ ((d >> 2) & 31)); }
+// residual element group: 16-byte chunk ch (dims 4ch..4ch+3) of frame f, XOR-swizzled so that both
+// "lanes = consecutive chunks of one frame" and "lanes = consecutive frames, one chunk" spread over banks
+__device__ __forceinline__ int rs_off(int f, int ch) { return f * 128 + ((ch ^ (f & 31)) << 2); }
+// byte offset inside a 128B-swizzled K block of dims 4g..4g+3 (g = 0..15) of row f
+__device__ __forceinline__ uint32_t asw_off(int f, int g) { return uint32_t(f * 128 + ((((g >> 1) ^ (f & 7))) << 4) + ((g & 1) << 3)); }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -78,6 +84,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
+}
+__device__ __forceinline__ float half_warp_sum(float v) {
+  #pragma unroll
+  for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
+  float t[11];
+  #pragma unroll
+  for (int j = 0; j < 10; ++j) t[j] = ptx::fmin3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+  t[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+  const float a = ptx::fmin3(t[0], t[1], t[2]), b = ptx::fmin3(t[3], t[4], t[5]), c = ptx::fmin3(t[6], t[7], t[8]);
+  return ptx::fmin3(ptx::fmin3(a, b, c), t[9], t[10]);
 }
 
 // tiles [start, start+cnt) of this CTA
@@ -88,6 +110,189 @@ __device__ __forceinline__ void cta_range(int64_t ntiles, int64_t& start, int64_
   cnt = base + (b < rem ? 1 : 0);
 }
 
+// ---- update pass -------------------------------------------------------------------------------------
+// torch's CPU argmax (core_vq.py:188) propagates NaN: the first NaN distance wins; otherwise the smallest
+// distance, lowest index on ties.  (best, bcode) starts as (+inf, 0x7fffffff).
+__device__ __forceinline__ bool nan_aware_better(float dist, int code, float best, int bcode) {
+  if (dist != dist) return best == best || code < bcode;
+  return best == best && (dist < best || (dist == best && code < bcode));
+}
+
+// Frames whose candidate set does not fit an Item (more than 4 candidates, or an exact scan): the whole
+// warp scores the set, one candidate per lane, and rewrites the frame's entry as a certified winner.
+__device__ __noinline__ void resolve_big(unsigned char* smem, int f, int lane, int K, int rot, const float* __restrict__ t32,
+                                         const float* __restrict__ cn) {
+  const float* rs = reinterpret_cast<const float*>(smem + SmemLayout::rs);
+  int* ncnt = reinterpret_cast<int*>(smem + SmemLayout::ncnt);
+  const bool full = ncnt[f] == kFull;
+  const uint32_t cm = full ? 0xffffffffu : *reinterpret_cast<const uint32_t*>(smem + SmemLayout::cmask + f * 4);
+  const uint32_t bm = full ? 0xffffffffu : *reinterpret_cast<const uint32_t*>(smem + SmemLayout::bmask + f * 4);
+  const int nc = __popc(cm);
+  const int total = full ? K : nc * __popc(bm);
+  // |r|^2: lane l owns chunk l
+  const float4 rl = *reinterpret_cast<const float4*>(rs + rs_off(f, lane));
+  const float rr = warp_sum(dot4(rl, rl, 0.f));
+  float best = inf_f(); int bcode = 0x7fffffff;
+  for (int t = lane; t < total; t += 32) {
+    int code;
+    if (full) code = t;
+    else {
+      const int a = int(__fns(bm, 0, t / nc + 1));       // batch in processing order -> actual batch
+      int pc = (a >> 2) + rot; pc = pc < (K >> 7) ? pc : pc - (K >> 7);
+      code = pc * 128 + (a & 3) * 32 + int(__fns(cm, 0, t % nc + 1));
+    }
+    if (code >= K) continue;
+    const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(code) * 128);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    #pragma unroll 2
+    for (int ch = 0; ch < 32; ch += 4) {
+      a0 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 0)), __ldg(rp + ch + 0), a0);
+      a1 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 1)), __ldg(rp + ch + 1), a1);
+      a2 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 2)), __ldg(rp + ch + 2), a2);
+      a3 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 3)), __ldg(rp + ch + 3), a3);
+    }
+    const float dot = (a0 + a1) + (a2 + a3);
+    const float dist = (rr - 2.f * dot) + __ldg(cn + code);          // core_vq.py:183-187
+    if (nan_aware_better(dist, code, best, bcode)) { best = dist; bcode = code; }
+  }
+  #pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oc = __shfl_xor_sync(0xffffffffu, bcode, off);
+    if (oc != 0x7fffffff && nan_aware_better(ob, oc, best, bcode)) { best = ob; bcode = oc; }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    *reinterpret_cast<int4*>(smem + SmemLayout::cand + f * 16) = make_int4(bcode == 0x7fffffff ? 0 : bcode, -1, -1, -1);
+    ncnt[f] = 1;
+  }
+  __syncwarp();
+}
+
+// Residual update of frame f by a half-warp (lane g owns dims 4g..4g+3 and 64+4g..64+4g+3): exact fp32
+// r <- r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training), fp16 operand of the
+// next stage, code store, squared-error partial.
+__device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem, int f, int g, float4 r0, float4 r1,
+                                          float4 q0, float4 q1, int code, int s, int64_t tile_n0, float& sq_acc) {
+  float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
+  if (p.ste) {                                   // core_vq.py:309
+    q0.x = r0.x + (q0.x - r0.x); q0.y = r0.y + (q0.y - r0.y); q0.z = r0.z + (q0.z - r0.z); q0.w = r0.w + (q0.w - r0.w);
+    q1.x = r1.x + (q1.x - r1.x); q1.y = r1.y + (q1.y - r1.y); q1.z = r1.z + (q1.z - r1.z); q1.w = r1.w + (q1.w - r1.w);
+  }
+  const float4 n0 = make_float4(r0.x - q0.x, r0.y - q0.y, r0.z - q0.z, r0.w - q0.w);
+  const float4 n1 = make_float4(r1.x - q1.x, r1.y - q1.y, r1.z - q1.z, r1.w - q1.w);
+  *reinterpret_cast<float4*>(rs + rs_off(f, g)) = n0;
+  *reinterpret_cast<float4*>(rs + rs_off(f, 16 + g)) = n1;
+  const int64_t n = tile_n0 + f;
+  if (n < p.N) {
+    if (g == 0) p.codes[int64_t(s) * p.N + n] = code;
+    if (p.sqerr != nullptr) sq_acc += dot4(n1, n1, dot4(n0, n0, 0.f));
+  }
+  const uint32_t ao = asw_off(f, g);
+  *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + ao) = make_uint2(pack_half2(n0.x, n0.y), pack_half2(n0.z, n0.w));
+  *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + 16384 + ao) = make_uint2(pack_half2(n1.x, n1.y), pack_half2(n1.z, n1.w));
+}
+
+// Re-score of one frame with up to 4 candidates by a half-warp: exact fp32 distances with the reference's
+// formula (core_vq.py:183-187), lowest index on ties; the winner's row is already in registers, so the
+// frame is updated right here.  `act` = this half-warp has a frame (the shuffles need all lanes).
+__device__ __forceinline__ void resolve_small(const TcParams& p, unsigned char* smem, int f, bool act, int g, int s,
+                                              int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn,
+                                              float& sq_acc) {
+  const float* rs = reinterpret_cast<const float*>(smem + SmemLayout::rs);
+  int c[4] = {-1, -1, -1, -1};
+  float4 row[4][2]; float cnv[4];
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+  if (act) {
+    const int4 cd = *reinterpret_cast<const int4*>(smem + SmemLayout::cand + f * 16);
+    c[0] = cd.x; c[1] = cd.y; c[2] = cd.z; c[3] = cd.w;
+    r0 = *reinterpret_cast<const float4*>(rs + rs_off(f, g));
+    r1 = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 + g));
+  }
+  #pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    row[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); row[u][1] = row[u][0]; cnv[u] = 0.f;
+    if (c[u] >= 0) {
+      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(c[u]) * 128);
+      row[u][0] = __ldg(rp + g); row[u][1] = __ldg(rp + 16 + g); cnv[u] = __ldg(cn + c[u]);
+    }
+  }
+  const float rr = half_warp_sum(dot4(r1, r1, dot4(r0, r0, 0.f)));
+  float dot[4];
+  #pragma unroll
+  for (int u = 0; u < 4; ++u) dot[u] = dot4(r1, row[u][1], dot4(r0, row[u][0], 0.f));
+  #pragma unroll
+  for (int off = 8; off > 0; off >>= 1) {
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], off);
+  }
+  float best = inf_f(); int bcode = c[0];
+  float4 q0 = row[0][0], q1 = row[0][1];
+  #pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float dist = (rr - 2.f * dot[u]) + cnv[u];
+    if (c[u] >= 0 && (dist < best || (dist == best && c[u] < bcode))) { best = dist; bcode = c[u]; q0 = row[u][0]; q1 = row[u][1]; }
+  }
+  if (act) apply_row(p, smem, f, g, r0, r1, q0, q1, bcode, s, tile_n0, sq_acc);
+}
+
+// One frame per half-warp.  FIRST: the residual rows were just loaded from x; only the fp16 operand is produced.
+template <bool FIRST>
+__device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* smem, int q, int h, int lane, int s, int rot,
+                                            int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn,
+                                            float& sq_acc, long long& t_mid) {
+  float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
+  const int hw = lane >> 4, g = lane & 15;
+  const int f16 = q * 32 + h * 16;                 // the 16 frames this warp owns
+  const int fb = f16 + hw * 8;                     // the 8 frames this half-warp updates
+  if (FIRST) {
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int f = fb + k;
+      const float4 n0 = *reinterpret_cast<const float4*>(rs + rs_off(f, g));
+      const float4 n1 = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 + g));
+      const uint32_t ao = asw_off(f, g);
+      *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + ao) = make_uint2(pack_half2(n0.x, n0.y), pack_half2(n0.z, n0.w));
+      *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + 16384 + ao) = make_uint2(pack_half2(n1.x, n1.y), pack_half2(n1.z, n1.w));
+    }
+    return;
+  }
+  const int nv = lane < 16 ? *reinterpret_cast<const int*>(smem + SmemLayout::ncnt + (f16 + lane) * 4) : 1;
+  uint32_t big = __ballot_sync(0xffffffffu, nv > 4);
+  const uint32_t slow = __ballot_sync(0xffffffffu, nv > 1);     // bit i = frame f16+i needs a re-score
+  // certified winners: all 8 rows of this half-warp go in flight before anything else
+  int code[8]; float4 qa[8], qb[8];
+  #pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    code[k] = *reinterpret_cast<const int*>(smem + SmemLayout::cand + (fb + k) * 16);
+    qa[k] = make_float4(0.f, 0.f, 0.f, 0.f); qb[k] = qa[k];
+    if (!((slow >> (hw * 8 + k)) & 1u)) {
+      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(code[k]) * 128);
+      qa[k] = __ldg(rp + g); qb[k] = __ldg(rp + 16 + g);
+    }
+  }
+  while (big) {                                      // wide candidate sets / exact scans -> a single winner
+    const int i = __ffs(big) - 1; big &= big - 1;
+    resolve_big(smem, f16 + i, lane, p.K, rot, t32, cn);
+  }
+  uint32_t todo = slow;                              // re-score + update, two frames per round
+  while (todo) {
+    const int i0 = __ffs(todo) - 1; todo &= todo - 1;
+    const int i1 = __ffs(todo) - 1; if (todo) todo &= todo - 1;
+    const int mine = hw == 0 ? i0 : i1;
+    resolve_small(p, smem, f16 + (mine < 0 ? 0 : mine), mine >= 0, g, s, tile_n0, t32, cn, sq_acc);
+  }
+  t_mid = clock64();
+  #pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if ((slow >> (hw * 8 + k)) & 1u) continue;
+    const int f = fb + k;
+    const float4 r0 = *reinterpret_cast<const float4*>(rs + rs_off(f, g));
+    const float4 r1 = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 + g));
+    apply_row(p, smem, f, g, r0, r1, qa[k], qb[k], code[k], s, tile_n0, sq_acc);
+  }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams p) {
@@ -95,36 +300,39 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   const uint32_t sbase = ptx::smem_u32(smem);
   Bars* bars = reinterpret_cast<Bars*>(smem + SmemLayout::bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = 128;
-  PackView pv(p.pack, p.K, D);
+  PackView pv(p.pack, p.K, 128);
   const int nchunks = p.K / kN;
+  // every CTA walks the chunks of a stage in its own rotation, so that the 148 SMs (which run the same stage
+  // at about the same time) do not all pull the same lines out of the same L2 slices at once
+  const int rot = int(blockIdx.x % unsigned(nchunks));
   const int64_t ntiles = (p.N + kM - 1) / kM;
   int64_t tile0, tcnt;
   cta_range(ntiles, tile0, tcnt);
-  const int rounds = int((tcnt + kGroups - 1) / kGroups);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1); }
-    for (int g = 0; g < kGroups; ++g) {
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->acc_full[g][i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[g][i]), 4); }
-      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[g]), kM);
-    }
+    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4); }
+    ptx::mbar_init(ptx::smem_u32(&bars->a_ready), 8);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {
+  // constant augmented K block of A: k-group 0 = (1, 1, 0, ...) picks up hi/lo of |c|^2, k-group 1 = 0
+  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
+    *reinterpret_cast<uint4*>(smem + SmemLayout::a_aug + i * 16) = make_uint4(i < 128 ? pack_half2(1.f, 1.f) : 0u, 0u, 0u, 0u);
+  if (warp == 9) {
     ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
     ptx::tmem_relinquish();
   }
+  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 0) {
-    // ===== TMA producer: one chunk stream (stage-major) per round, shared by both tile slots =====
+  if (warp == 8) {
+    // ===== TMA producer: the chunk stream (stage-major) of every tile =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int r = 0; r < rounds; ++r) {
+      for (int64_t t = 0; t < tcnt; ++t) {
         for (int s = 0; s < p.n_q; ++s) {
           const unsigned char* img = pv.tc(p.stage0 + s);
           for (int c = 0; c < nchunks; ++c, ++it) {
@@ -132,306 +340,251 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), ph ^ 1);
             const uint32_t fb = ptx::smem_u32(&bars->full[slot]);
             ptx::mbar_expect_tx(fb, kTcChunkBytes);
-            ptx::bulk_g2s(sbase + SmemLayout::b + slot * kTcChunkBytes, img + size_t(c) * kTcChunkBytes, kTcChunkBytes, fb);
+            const int pc = c + rot < nchunks ? c + rot : c + rot - nchunks;
+            ptx::bulk_g2s(sbase + SmemLayout::b + slot * kTcChunkBytes, img + size_t(pc) * kTcChunkBytes, kTcChunkBytes, fb);
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
-      uint32_t it = 0, ait = 0, acc_it[kGroups] = {0, 0};
-      for (int r = 0; r < rounds; ++r) {
-        const bool act1 = int64_t(r) * kGroups + 1 < tcnt;       // slot 1 idle in an odd last round
-        for (int s = 0; s < p.n_q; ++s, ++ait) {
-          for (int c = 0; c < nchunks; ++c, ++it) {
-            const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-            ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), ph);                 // codebook chunk landed
-            const uint32_t b_addr = sbase + SmemLayout::b + slot * kTcChunkBytes;
-            #pragma unroll
-            for (int g = 0; g < kGroups; ++g) {
-              if (g == 1 && !act1) continue;
-              if (c == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[g]), ait & 1);   // fp16 residual operand in TMEM
-              const uint32_t buf = acc_it[g] & 1, aph = (acc_it[g] >> 1) & 1;
-              ++acc_it[g];
-              ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[g][buf]), aph ^ 1);   // frame threads drained this buffer
-              ptx::tc_fence_after();
-              const uint32_t d_tmem = tmem + g * kTmemSlot + buf * kN;
-              const uint32_t a_tmem = tmem + g * kTmemSlot + kTmemA;
-              #pragma unroll
-              for (int k = 0; k < kKSteps; ++k) {
-                const uint64_t bd = ptx::umma_desc_kmajor_noswz(b_addr + k * 2 * kTcLBO, kTcLBO, kTcSBO);
-                ptx::umma_f16_ts(d_tmem, a_tmem + k * 8, bd, idesc, k > 0 ? 1u : 0u);
-              }
-              ptx::umma_commit(ptx::smem_u32(&bars->acc_full[g][buf]));   // scores ready for the frame threads
-            }
-            ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));          // ring slot reusable once read
-          }
+  } else if (warp >= 9) {
+    // ===== MMA issuers: descriptors hoisted, 9 MMAs + 2 commits per 128-code chunk.  The issue path of one
+    // thread (two barrier waits of ~100 cycles each + the scalar code around every tcgen05.mma) is longer than
+    // the 576 tensor cycles of a chunk, so two warps alternate chunks (even / odd). =====
+    const uint32_t who = warp - 9;
+    const uint32_t stride = nchunks >= 2 ? 2u : 1u;
+    if (lane == 0 && who < stride) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
+      uint64_t ad[kKSteps];
+      #pragma unroll
+      for (int k = 0; k < 8; ++k) ad[k] = ptx::umma_desc_kmajor_sw128(sbase + SmemLayout::a_sw + (k >> 2) * 16384 + (k & 3) * 32);
+      ad[8] = ptx::umma_desc_kmajor_noswz(sbase + SmemLayout::a_aug, 2048, 128);
+      const uint64_t bd0 = ptx::umma_desc_kmajor_noswz(sbase + SmemLayout::b, kTcLBO, kTcSBO);
+      const uint32_t total = uint32_t(tcnt) * uint32_t(p.n_q) * uint32_t(nchunks);
+      uint32_t seen = 0xffffffffu;          // last (tile, stage) index whose operand this thread waited for
+      long long w_a = 0, w_bar = 0, w_issue = 0, tm0 = clock64();
+      const long long tm_begin = tm0;
+      for (uint32_t it = who; it < total; it += stride) {
+        const uint32_t ar = it / uint32_t(nchunks);
+        if (ar != seen) {
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), ar & 1);                 // fp16 residual operand written
+          seen = ar;
+          { const long long tt = clock64(); w_a += tt - tm0; tm0 = tt; }
         }
+        const uint32_t slot = it % kRing, buf = it % kAccBufs;
+        ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), (it / kRing) & 1);              // codebook chunk landed
+        ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), ((it / kAccBufs) & 1) ^ 1); // accumulator drained
+        ptx::tc_fence_after();
+        { const long long tt = clock64(); w_bar += tt - tm0; tm0 = tt; }
+        const uint32_t d_tmem = tmem + buf * kN;
+        const uint64_t b0 = bd0 + uint64_t((slot * kTcChunkBytes) >> 4);
+        #pragma unroll
+        for (int k = 0; k < kKSteps; ++k)
+          ptx::umma_f16_ss(d_tmem, ad[k], b0 + uint64_t((k * 2 * kTcLBO) >> 4), idesc, k > 0 ? 1u : 0u);
+        ptx::umma_commit(ptx::smem_u32(&bars->acc_full[buf]));     // scores ready for the score warps
+        ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));       // ring slot reusable once read
+        { const long long tt = clock64(); w_issue += tt - tm0; tm0 = tt; }
+      }
+      if (p.counters != nullptr && who == 0) {
+        atomicAdd(&p.counters[11], (unsigned long long)w_a); atomicAdd(&p.counters[12], (unsigned long long)w_bar);
+        atomicAdd(&p.counters[13], 0ull); atomicAdd(&p.counters[14], (unsigned long long)(clock64() - tm_begin));
+        atomicAdd(&p.counters[19], (unsigned long long)w_issue);
       }
     }
     __syncwarp();
   } else {
-    // ===== frame threads: thread <-> TMEM lane <-> frame of the slot's tile =====
-    const int g = (warp - 2) >> 2;             // tile slot
-    const int wq = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int f = wq * 32 + lane;              // frame row within the tile
-    const uint32_t tlane = tmem + g * kTmemSlot + (uint32_t(wq * 32) << 16);
-    float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs) + g * 128 * kM;
-    float* sbmin = reinterpret_cast<float*>(smem + SmemLayout::bmin) + g * kMaxBatches * kM;
-    uint32_t* wlist = reinterpret_cast<uint32_t*>(smem + SmemLayout::list) + (warp - 2) * kListMax;
-    const uint32_t bar_a = ptx::smem_u32(&bars->a_ready[g]);
-    // augmented K columns never change: cols 128,129 = 1 (pick up hi/lo of |c|^2), rest 0
-    {
-      uint32_t w8[8] = {pack_half2(1.f, 1.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      ptx::tmem_st8(tlane + kTmemA + 64, w8);
-    }
+    // ===== frame warps =====
+    const int q = warp & 3;                    // TMEM lane quadrant = frames 32q..32q+31 of the tile
+    const int h = warp >= 4 ? 1 : 0;           // 0 = score warp, 1 = helper warp
+    const int f = q * 32 + lane;               // tile load / score mapping: thread <-> frame
+    const uint32_t pair_bar = 1 + q;
+    const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);
+    float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
+    float* xpart = reinterpret_cast<float*>(smem + SmemLayout::xpart);
+    const uint32_t bar_a = ptx::smem_u32(&bars->a_ready);
     unsigned long long n_cert = 0, n_resc = 0, n_full = 0, n_all = 0;
-    long long t_wait = 0, t_epi = 0, t_win = 0, t_upd = 0, t_load = 0;   // phase cycles (lane 0 of each warp)
+    long long t_wait = 0, t_epi = 0, t_win = 0, t_upd = 0, t_load = 0, t_res = 0, t_bar = 0;   // phase cycles (lane 0 of each score warp)
     const long long t_begin = clock64();
     uint32_t acc_it = 0;
-    for (int r = 0; r < rounds; ++r) {
-      if (int64_t(r) * kGroups + g >= tcnt) break;     // idle slot in the last round
-      const int64_t tile = tile0 + int64_t(r) * kGroups + g;
-      const int64_t n = tile * kM + f;
-      const bool valid = n < p.N;
+    for (int64_t t = 0; t < tcnt; ++t) {
+      const int64_t tile_n0 = (tile0 + t) * kM;
       long long tc0 = clock64();
-      // ---- load the latent, |x|^2 with the exact path's summation order, fp16 operand row ----
-      float xx;
+      // ---- load the latent tile: this warp takes dims 64h..64h+63 of its quadrant's 32 frames ----
       {
+        const int64_t n = tile_n0 + f;
+        const bool valid = n < p.N;
         const int64_t xb = valid ? p.fa.base(n) : 0;
-        float part[4] = {0.f, 0.f, 0.f, 0.f};
         #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+        for (int hb = 0; hb < 2; ++hb) {
           float v[32];
+          const int d0 = h * 64 + hb * 32;
           #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = valid ? __ldg(p.x + xb + int64_t(h * 32 + j) * p.fa.sxd) : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = valid ? __ldg(p.x + xb + int64_t(d0 + j) * p.fa.sxd) : 0.f;
+          float part = 0.f;
           #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            rs[rs_idx(h * 32 + j, f)] = v[j];
-            part[h] = fmaf(v[j], v[j], part[h]);
+          for (int j = 0; j < 32; j += 4) {
+            *reinterpret_cast<float4*>(rs + rs_off(f, (d0 + j) >> 2)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            part = fmaf(v[j], v[j], part); part = fmaf(v[j + 1], v[j + 1], part);
+            part = fmaf(v[j + 2], v[j + 2], part); part = fmaf(v[j + 3], v[j + 3], part);
           }
-          uint32_t w0[8], w1[8];
-          #pragma unroll
-          for (int j = 0; j < 8; ++j) { w0[j] = pack_half2(v[2 * j], v[2 * j + 1]); w1[j] = pack_half2(v[16 + 2 * j], v[17 + 2 * j]); }
-          ptx::tmem_st8(tlane + kTmemA + h * 16, w0);
-          ptx::tmem_st8(tlane + kTmemA + h * 16 + 8, w1);
+          xpart[(h * 2 + hb) * kM + f] = part;
         }
-        xx = ((part[0] + part[1]) + part[2]) + part[3];
       }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(bar_a);
-      { const long long t = clock64(); t_load += t - tc0; tc0 = t; }
+      ptx::named_bar_sync(pair_bar, 64);
+      float xx = ((xpart[f] + xpart[kM + f]) + xpart[2 * kM + f]) + xpart[3 * kM + f];   // exact path's order
+      float sq_dummy = 0.f;
+      long long t_mid = 0;
+      update_pass<true>(p, smem, q, h, lane, 0, rot, tile_n0, nullptr, nullptr, sq_dummy, t_mid);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_a);
+      { const long long tt = clock64(); t_load += tt - tc0; tc0 = tt; }
 
       for (int s = 0; s < p.n_q; ++s) {
         const int st = p.stage0 + s;
-        const StageMeta* meta = pv.meta(st);
-        const float xnorm = sqrtf(xx);
-        const float delta = meta->margin_coef * (xnorm + 1e-3f) + meta->margin_abs;
-        const bool outl = !(xnorm < meta->xlimit);      // also true for NaN
-        float cm[32];
-        #pragma unroll
-        for (int j = 0; j < 32; ++j) cm[j] = inf_f();
-
-        for (int c = 0; c < nchunks; ++c, ++acc_it) {
-          const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
-          ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[g][buf]), aph);
-          ptx::tc_fence_after();
-          { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
-          {
-            uint32_t v0[32], v1[32];
-            ptx::tmem_ld32(tlane + buf * kN, v0);
-            ptx::tmem_ld32(tlane + buf * kN + 32, v1);
-            ptx::tmem_ld_wait();
-            // scores are in registers: hand the accumulator back before reducing them
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[g][buf]));
-            #pragma unroll
-            for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
-            float t0[11], t1[11];
-            #pragma unroll
-            for (int j = 0; j < 10; ++j) {
-              t0[j] = ptx::fmin3(__uint_as_float(v0[3 * j]), __uint_as_float(v0[3 * j + 1]), __uint_as_float(v0[3 * j + 2]));
-              t1[j] = ptx::fmin3(__uint_as_float(v1[3 * j]), __uint_as_float(v1[3 * j + 1]), __uint_as_float(v1[3 * j + 2]));
-            }
-            t0[10] = fminf(__uint_as_float(v0[30]), __uint_as_float(v0[31]));
-            t1[10] = fminf(__uint_as_float(v1[30]), __uint_as_float(v1[31]));
-            float b0 = ptx::fmin3(ptx::fmin3(t0[0], t0[1], t0[2]), ptx::fmin3(t0[3], t0[4], t0[5]), ptx::fmin3(t0[6], t0[7], t0[8]));
-            float b1 = ptx::fmin3(ptx::fmin3(t1[0], t1[1], t1[2]), ptx::fmin3(t1[3], t1[4], t1[5]), ptx::fmin3(t1[6], t1[7], t1[8]));
-            b0 = ptx::fmin3(b0, t0[9], t0[10]);
-            b1 = ptx::fmin3(b1, t1[9], t1[10]);
-            sbmin[(c * 2) * kM + f] = b0;
-            sbmin[(c * 2 + 1) * kM + f] = b1;
-          }
-          { const long long t = clock64(); t_epi += t - tc0; tc0 = t; }
-        }
-
-        // ---- winner: certified / re-scored / exact scan ----
-        float m = inf_f();
-        #pragma unroll
-        for (int j = 0; j < 32; j += 2) m = ptx::fmin3(m, cm[j], cm[j + 1]);
-        const float thr = m + delta;
-        uint32_t cmask = 0, bmask = 0;
-        #pragma unroll
-        for (int j = 0; j < 32; ++j) cmask |= (cm[j] <= thr) ? (1u << j) : 0u;
-        const int nb = nchunks * 2;
-        for (int a = 0; a < nb; ++a) bmask |= (sbmin[a * kM + f] <= thr) ? (1u << a) : 0u;
-        const int ncl = __popc(cmask), nba = __popc(bmask);
         const float* t32 = pv.tab32(st);
         const float* cn = pv.cnorm(st);
-        int idx = 0;
-        bool need_full = outl || cmask == 0u || bmask == 0u;       // masks are empty only for NaN scores
-        const bool certified = !need_full && ncl == 1 && nba == 1;
-        if (certified) { idx = (__ffs(bmask) - 1) * 32 + (__ffs(cmask) - 1); ++n_cert; }
-        const bool need_resc = !need_full && !certified;
-        const uint32_t resc_mask = __ballot_sync(0xffffffffu, need_resc);
-        if (resc_mask != 0u) {
-          // candidates = flagged batches x flagged classes.  All lanes' candidates go to one list
-          // (ascending code order per frame) that the warp then scores cooperatively: lane l holds
-          // dims 4l..4l+3 of the code row (coalesced 512-B read) and of the frame's residual.
-          const int mine = need_resc ? ncl * nba : 0;
-          int pre = mine;
+        if (h == 0) {
+          // ---- scores: per-class and per-batch minima of the K approximate scores of this frame ----
+          const StageMeta* meta = pv.meta(st);
+          const float xnorm = sqrtf(xx);
+          const float delta = meta->margin_coef * (xnorm + 1e-3f) + meta->margin_abs;
+          const bool outl = !(xnorm < meta->xlimit);      // also true for NaN
+          float cm[32], bmin[32];
           #pragma unroll
-          for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, pre, off); if (lane >= off) pre += o; }
-          const int total = __shfl_sync(0xffffffffu, pre, 31);
-          if (total > kListMax) {
-            if (need_resc) need_full = true;           // pathological tie width: exact scan instead
-          } else {
-            int pos = pre - mine;
-            if (need_resc) {
-              uint32_t bm2 = bmask;
-              while (bm2) {
-                const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
-                uint32_t cm2 = cmask;
-                while (cm2) { const int j = __ffs(cm2) - 1; cm2 &= cm2 - 1; wlist[pos++] = (uint32_t(lane) << 16) | uint32_t(a * 32 + j); }
-              }
-            }
-            __syncwarp();
-            float best = inf_f(); int bi = 0x7fffffff;
-            for (int e0 = 0; e0 < total; e0 += 4) {
-              float part[4], xxo[4]; int code[4], own[4];
-              #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint32_t ent = wlist[min(e0 + u, total - 1)];
-                own[u] = int(ent >> 16); code[u] = int(ent & 0xffffu);
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(t32 + size_t(code[u]) * D) + lane);
-                const int fo = wq * 32 + own[u];
-                float acc = rs[rs_idx(4 * lane + 0, fo)] * cv.x;
-                acc = fmaf(rs[rs_idx(4 * lane + 1, fo)], cv.y, acc);
-                acc = fmaf(rs[rs_idx(4 * lane + 2, fo)], cv.z, acc);
-                acc = fmaf(rs[rs_idx(4 * lane + 3, fo)], cv.w, acc);
-                part[u] = acc;
-                xxo[u] = __shfl_sync(0xffffffffu, xx, own[u]);
-              }
-              #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float dot = warp_sum(part[u]);
-                const float dist = (xxo[u] - 2.f * dot) + __ldg(cn + code[u]);      // core_vq.py:183-187
-                if (e0 + u < total && lane == own[u] && dist < best) { best = dist; bi = code[u]; }
-              }
-            }
-            if (need_resc) { idx = bi == 0x7fffffff ? 0 : bi; ++n_resc; }
-            __syncwarp();
-          }
-        }
-        if (__any_sync(0xffffffffu, need_full)) {
-          // frames outside the fp16 image's validity range, NaN, or absurd tie widths: exact fp32
-          // scan of the whole table, all lanes in lockstep (code rows are warp-uniform loads)
-          float best = inf_f(); int bi = 0x7fffffff;
-          for (int k = 0; k < p.K; ++k) {
-            const float4* row = reinterpret_cast<const float4*>(t32 + size_t(k) * D);
-            float acc = 0.f;
-            #pragma unroll 4
-            for (int d4 = 0; d4 < 32; ++d4) {
-              const float4 cv = __ldg(row + d4);
-              acc = fmaf(rs[rs_idx(d4 * 4 + 0, f)], cv.x, acc);
-              acc = fmaf(rs[rs_idx(d4 * 4 + 1, f)], cv.y, acc);
-              acc = fmaf(rs[rs_idx(d4 * 4 + 2, f)], cv.z, acc);
-              acc = fmaf(rs[rs_idx(d4 * 4 + 3, f)], cv.w, acc);
-            }
-            const float dist = (xx - 2.f * acc) + __ldg(cn + k);
-            if (dist < best) { best = dist; bi = k; }
-          }
-          if (need_full) { idx = bi == 0x7fffffff ? 0 : bi; ++n_full; }
-        }
-        ++n_all;
-        { const long long t = clock64(); t_win += t - tc0; tc0 = t; }
-
-        // ---- gather the fp32 row, exact residual update, next stage's fp16 operand ----
-        {
-          const float4* row = reinterpret_cast<const float4*>(t32 + size_t(idx) * D);
-          float part[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < 32; ++j) { cm[j] = inf_f(); bmin[j] = inf_f(); }
           #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            float4 cq[8];
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) cq[j] = __ldg(row + h * 8 + j);
-            uint32_t w0[8], w1[8];
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float cv[4] = {cq[j].x, cq[j].y, cq[j].z, cq[j].w};
-              float rn[4];
+          for (int c = 0; c < kMaxChunks; ++c) {
+            if (c < nchunks) {
+              const uint32_t buf = acc_it % kAccBufs, aph = (acc_it / kAccBufs) & 1;
+              ++acc_it;
+              ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), aph);
+              ptx::tc_fence_after();
+              { const long long tt = clock64(); t_wait += tt - tc0; tc0 = tt; }
+              uint32_t v0[32], v1[32];
+              ptx::tmem_ld32(tlane + buf * kN, v0);
+              ptx::tmem_ld32(tlane + buf * kN + 32, v1);
+              ptx::tmem_ld_wait();
               #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int d = h * 32 + j * 4 + i;
-                const float rv = rs[rs_idx(d, f)];
-                float qv = cv[i];
-                if (p.ste) qv = rv + (qv - rv);               // core_vq.py:309
-                rn[i] = rv - qv;                               // core_vq.py:364 / :348
-                rs[rs_idx(d, f)] = rn[i];
-                part[h] = fmaf(rn[i], rn[i], part[h]);
-              }
-              if (j < 4) { w0[2 * j] = pack_half2(rn[0], rn[1]); w0[2 * j + 1] = pack_half2(rn[2], rn[3]); }
-              else       { w1[2 * (j - 4)] = pack_half2(rn[0], rn[1]); w1[2 * (j - 4) + 1] = pack_half2(rn[2], rn[3]); }
+              for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+              bmin[c * 4 + 0] = min32(v0);
+              bmin[c * 4 + 1] = min32(v1);
+              ptx::tmem_ld32(tlane + buf * kN + 64, v0);
+              ptx::tmem_ld32(tlane + buf * kN + 96, v1);
+              ptx::tmem_ld_wait();
+              // scores are in registers: hand the accumulator back before reducing them
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));
+              #pragma unroll
+              for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+              bmin[c * 4 + 2] = min32(v0);
+              bmin[c * 4 + 3] = min32(v1);
+              { const long long tt = clock64(); t_epi += tt - tc0; tc0 = tt; }
             }
-            ptx::tmem_st8(tlane + kTmemA + h * 16, w0);
-            ptx::tmem_st8(tlane + kTmemA + h * 16 + 8, w1);
           }
-          xx = ((part[0] + part[1]) + part[2]) + part[3];
+          // ---- candidates: certified winner / up to 4 codes to re-score / mask enumeration / exact scan ----
+          float m4[4];
+          #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m4[j] = ptx::fmin3(cm[8 * j], cm[8 * j + 1], cm[8 * j + 2]);
+            m4[j] = ptx::fmin3(m4[j], cm[8 * j + 3], cm[8 * j + 4]);
+            m4[j] = ptx::fmin3(m4[j], cm[8 * j + 5], cm[8 * j + 6]);
+            m4[j] = fminf(m4[j], cm[8 * j + 7]);
+          }
+          const float m = fminf(ptx::fmin3(m4[0], m4[1], m4[2]), m4[3]);
+          const float thr = m + delta;
+          uint32_t cm4[4] = {0u, 0u, 0u, 0u}, bm4[4] = {0u, 0u, 0u, 0u};
+          #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            cm4[j & 3] |= (cm[j] <= thr) ? (1u << j) : 0u;
+            bm4[j & 3] |= (bmin[j] <= thr) ? (1u << j) : 0u;
+          }
+          const uint32_t cmask = (cm4[0] | cm4[1]) | (cm4[2] | cm4[3]), bmask = (bm4[0] | bm4[1]) | (bm4[2] | bm4[3]);
+          const int nc = __popc(cmask), nb = __popc(bmask);
+          const bool full = outl || cmask == 0u || bmask == 0u;     // masks are empty only for NaN scores
+          const int ncand = nc * nb;
+          // bmask bit a = a-th batch in this CTA's processing order; its codes start at batch_base(a)
+          auto batch_base = [&](int a) { int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks; return pc * 128 + (a & 3) * 32; };
+          int4 cd = make_int4(batch_base(__ffs(bmask) - 1) + (__ffs(cmask) - 1), -1, -1, -1);
+          if (!full && ncand > 1 && ncand <= 4) {
+            int cc[4] = {-1, -1, -1, -1};
+            int w = 0;
+            uint32_t bm2 = bmask;
+            while (bm2) {
+              const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
+              uint32_t cm2 = cmask;
+              while (cm2) {
+                const int j = __ffs(cm2) - 1; cm2 &= cm2 - 1;
+                const int code = batch_base(a) + j;
+                if (w == 0) cc[0] = code; else if (w == 1) cc[1] = code; else if (w == 2) cc[2] = code; else cc[3] = code;
+                ++w;
+              }
+            }
+            cd = make_int4(cc[0], cc[1], cc[2], cc[3]);
+          }
+          *reinterpret_cast<int4*>(smem + SmemLayout::cand + f * 16) = cd;
+          *reinterpret_cast<int*>(smem + SmemLayout::ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
+          *reinterpret_cast<uint32_t*>(smem + SmemLayout::cmask + f * 4) = cmask;
+          *reinterpret_cast<uint32_t*>(smem + SmemLayout::bmask + f * 4) = bmask;
+          ++n_all;
+          if (full) ++n_full; else if (ncand == 1) ++n_cert; else ++n_resc;
+          // upper bound of the next residual's |r|^2 (only the margin and the validity test use it):
+          // the winner's approximate score is <= m + delta and off by <= delta/2
+          if (full) { const float g2 = xnorm + meta->cmax_all; xx = g2 * g2; }
+          else xx = fmaxf(xx + m + 1.5f * delta, 0.f) * 1.00001f + 1e-30f;
         }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        if (s + 1 < p.n_q) ptx::mbar_arrive(bar_a);
-        if (valid) p.codes[int64_t(s) * p.N + n] = idx;
+        { const long long tt = clock64(); t_win += tt - tc0; tc0 = tt; }
+        ptx::named_bar_sync(pair_bar, 64);       // candidate lists visible to both warps of the quadrant
+        { const long long tt = clock64(); t_bar += tt - tc0; tc0 = tt; }
+        float sq = 0.f;
+        update_pass<false>(p, smem, q, h, lane, s, rot, tile_n0, t32, cn, sq, t_mid);
+        t_res += t_mid - tc0;
+        if (s + 1 < p.n_q) {
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_a);
+        }
         if (p.sqerr != nullptr) {
-          const float v = warp_sum(valid ? xx : 0.f);
-          if (lane == 0) atomicAdd(&p.sqerr[s], (double)v);
+          sq = warp_sum(sq);
+          if (lane == 0) atomicAdd(&p.sqerr[s], (double)sq);
         }
-        { const long long t = clock64(); t_upd += t - tc0; tc0 = t; }
+        { const long long tt = clock64(); t_upd += tt - tc0; tc0 = tt; }
       }
-      if (p.residual_out != nullptr && valid) {
-        float* out = p.residual_out + n * D;
-        #pragma unroll 4
-        for (int d4 = 0; d4 < 32; ++d4)
-          *reinterpret_cast<float4*>(out + d4 * 4) = make_float4(rs[rs_idx(d4 * 4, f)], rs[rs_idx(d4 * 4 + 1, f)],
-                                                                 rs[rs_idx(d4 * 4 + 2, f)], rs[rs_idx(d4 * 4 + 3, f)]);
+      if (p.residual_out != nullptr) {
+        // each warp writes the 16 frames it owns, 512 contiguous bytes per frame
+        for (int i = 0; i < 16; ++i) {
+          const int fo = q * 32 + h * 16 + i;
+          const int64_t n = tile_n0 + fo;
+          if (n < p.N) *reinterpret_cast<float4*>(p.residual_out + n * 128 + lane * 4) = *reinterpret_cast<const float4*>(rs + rs_off(fo, lane));
+        }
       }
+      ptx::named_bar_sync(pair_bar, 64);         // both warps are done with this tile's rows
     }
     // search statistics and phase cycles (evidence; see rvq_search_stats)
-    #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      n_all += __shfl_xor_sync(0xffffffffu, n_all, off);
-      n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
-      n_resc += __shfl_xor_sync(0xffffffffu, n_resc, off);
-      n_full += __shfl_xor_sync(0xffffffffu, n_full, off);
-    }
-    if (lane == 0 && p.counters != nullptr) {
-      atomicAdd(&p.counters[0], n_all); atomicAdd(&p.counters[1], n_cert);
-      atomicAdd(&p.counters[2], n_resc); atomicAdd(&p.counters[3], n_full);
-      atomicAdd(&p.counters[4], (unsigned long long)t_wait); atomicAdd(&p.counters[5], (unsigned long long)t_epi);
-      atomicAdd(&p.counters[6], (unsigned long long)t_win);  atomicAdd(&p.counters[7], (unsigned long long)t_upd);
-      atomicAdd(&p.counters[8], (unsigned long long)t_load); atomicAdd(&p.counters[9], (unsigned long long)(clock64() - t_begin));
-      atomicAdd(&p.counters[10], 1ull);
+    if (h == 0) {
+      #pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        n_all += __shfl_xor_sync(0xffffffffu, n_all, off);
+        n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
+        n_resc += __shfl_xor_sync(0xffffffffu, n_resc, off);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, off);
+      }
+      if (lane == 0 && p.counters != nullptr) {
+        atomicAdd(&p.counters[0], n_all); atomicAdd(&p.counters[1], n_cert);
+        atomicAdd(&p.counters[2], n_resc); atomicAdd(&p.counters[3], n_full);
+        atomicAdd(&p.counters[4], (unsigned long long)t_wait); atomicAdd(&p.counters[5], (unsigned long long)t_epi);
+        atomicAdd(&p.counters[6], (unsigned long long)t_win);  atomicAdd(&p.counters[7], (unsigned long long)t_upd);
+        atomicAdd(&p.counters[8], (unsigned long long)t_load); atomicAdd(&p.counters[9], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&p.counters[10], 1ull);
+        atomicAdd(&p.counters[15], (unsigned long long)t_res); atomicAdd(&p.counters[16], (unsigned long long)t_bar);
+      }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+  if (warp == 9) ptx::tmem_dealloc(tmem, 512);
 }
 
 int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa, int64_t N, int T, int stage0, int n_q,
@@ -450,7 +603,7 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
     sm_dev = dev;
   }
   PackView pv(a.pack, a.K, a.D);
-  RVQ_CUDA(cudaMemsetAsync(pv.counters(), 0, 16 * sizeof(unsigned long long), st));
+  RVQ_CUDA(cudaMemsetAsync(pv.counters(), 0, 32 * sizeof(unsigned long long), st));
   TcParams p;
   p.pack = (const unsigned char*)a.pack; p.K = a.K;
   p.x = a.x; p.fa = FrameAddr{a.sxb, a.sxd, a.sxt, a.T}; p.N = N;
@@ -459,8 +612,7 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   p.ste = (a.flags & RVQ_FLAG_STE) ? 1 : 0;
   p.counters = pv.counters();
   const int64_t ntiles = (N + kM - 1) / kM;
-  const int64_t pairs = (ntiles + kGroups - 1) / kGroups;
-  const unsigned grid = unsigned(pairs < sm_count ? pairs : sm_count);
+  const unsigned grid = unsigned(ntiles < sm_count ? ntiles : sm_count);
   tc_encode_kernel<<<grid, kThreadsTc, SmemLayout::total, st>>>(p);
   RVQ_LAUNCH_CHECK("tc_encode_kernel");
   if (a.quantized != nullptr)

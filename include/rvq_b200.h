@@ -134,7 +134,7 @@ int rvq_residual_combine(const void* pack, int K, int D,
                          float* out, int flags, void* stream);
 
 /* ---- debug / evidence: counters of the tcgen05 search written by the last rvq_encode on
- * `stream`-ordered memory inside the pack.  out_host: 16 x uint64:
+ * `stream`-ordered memory inside the pack.  out_host: 32 x uint64:
  *   [0] frame-stages searched, [1] certified unique, [2] re-scored candidates, [3] exact scans,
  *   [4..9] summed frame-warp cycles: waiting for scores, reading/min-reducing scores, choosing
  *   the winner, residual update, tile load, total; [10] frame warps counted.
