@@ -226,5 +226,5 @@ def search_stats(pk: CodebookPack) -> tp.Dict[str, int]:
     with _guard(pk.device):
         L.check(lib.rvq_search_stats(pk.buf.data_ptr(), arr, L.stream_ptr(pk.device)), "rvq_search_stats")
     names = ("searched", "certified", "rescored", "fullscan", "cyc_wait", "cyc_scores", "cyc_winner", "cyc_update",
-             "cyc_load", "cyc_total", "warps", "mma_wait_a", "mma_wait_full", "mma_wait_acc", "mma_total", "cyc_resolve", "cyc_pairbar", "tma_late_lat_sum", "tma_late_n", "mma_issue")
+             "cyc_load", "cyc_total", "warps", "mma_wait_a", "mma_wait_full", "mma_wait_acc", "mma_total", "cyc_resolve", "cyc_pairbar", "tma_late_lat_sum", "tma_late_n", "mma_issue", "cand2", "cand3_4", "cand5_8", "cand9plus")
     return {n: int(arr[i]) for i, n in enumerate(names)}

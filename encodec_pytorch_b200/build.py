@@ -35,7 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    defs = [f"-D{d}" for d in os.environ.get("RVQ_NVCC_DEFS", "").split() if d]   # e.g. RVQ_TC_TRACE RVQ_TC_TIMERS
+    cmd = [nvcc, *NVCC_FLAGS, *defs, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

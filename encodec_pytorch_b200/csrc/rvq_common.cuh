@@ -119,5 +119,6 @@ struct EncodeArgs {
 int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st);
 int simt_encode(const EncodeArgs& a, cudaStream_t st);
 int tc_encode(const EncodeArgs& a, cudaStream_t st);
+int tc_debug_trace(long long* out_host, int n);
 
 }  // namespace rvq

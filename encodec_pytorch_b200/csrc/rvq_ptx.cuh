@@ -164,6 +164,10 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- register re-balancing between warpgroups (every warp of the warpgroup must execute it) -------------
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- 3-input float min (FMNMX3 on sm_100) ----------------------------------------------------------
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float d;

@@ -9,6 +9,7 @@
 //   quantization/core_vq.py:227-235  EMA statistics, Laplace smoothing, table overwrite
 //   quantization/core_vq.py:80-102   k-means
 #include "rvq_common.cuh"
+#include <stdlib.h>
 
 namespace rvq {
 
@@ -49,7 +50,7 @@ constexpr float kOutlierMul = 64.f;                  // codes with |c| > 64 * me
 constexpr float kBigScore   = 60000.f;               // fp16-representable score of an outlier code
 constexpr float kHalfSafe   = 3.0e4f;                // |2c| elements and |c|^2 must stay below fp16 max
 
-__global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, int stage_base, int K, int D) {
+__global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, int stage_base, int K, int D, float margin_scale) {
   extern __shared__ float sh[];          // [Kpow2] sorted norms, then [K] flags
   const int s = stage_base + blockIdx.x;
   PackView pv(pack, K, D);
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     StageMeta m;
     m.cref = s_cref; m.cmin = s_cmin; m.n_outliers = s_nout;
     m.cmax_all = s_cmax; m.reserved = 0;
-    m.margin_coef = 2.f * kBetaFp16 * (s_cref + kEps1);
+    m.margin_coef = margin_scale * 2.f * kBetaFp16 * (s_cref + kEps1);
     // |c|^2 is carried as fp16 hi + fp16 lo: error <= 2^-22 |c|^2 (+ 2^-24 when lo is subnormal)
     m.margin_abs = 2.f * (2.4e-7f * s_cref * s_cref + 6e-8f);
     // |x| bound under which (a) outlier codes provably lose to the smallest-norm code and
@@ -167,6 +168,9 @@ int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* 
   RVQ_REQUIRE(meta_smem <= 200 * 1024, "rvq_pack: codebook_size %d too large", K);
   RVQ_CUDA(cudaFuncSetAttribute(pack_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta_smem));
   RVQ_CUDA(cudaMemsetAsync(pack, 0, kHeaderBytes, st));
+  // experiment knob (NOT rigorous below 1): scales the fp16 score-error margin to study its effect on the re-score rate
+  float margin_scale = 1.f;
+  if (const char* e = getenv("RVQ_MARGIN_SCALE")) margin_scale = (float)atof(e);
   for (int s0 = 0; s0 < n_q; s0 += 32) {
     int ns = n_q - s0 < 32 ? n_q - s0 : 32;
     PtrTable32 tab;
@@ -174,7 +178,7 @@ int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* 
     dim3 grid((D + 31) / 32, (K + 31) / 32, ns), block(32, 8);
     pack_copy_kernel<<<grid, block, 0, st>>>(tab, (unsigned char*)pack, s0, K, D);
     RVQ_LAUNCH_CHECK("pack_copy_kernel");
-    pack_meta_kernel<<<ns, 1024, meta_smem, st>>>((unsigned char*)pack, s0, K, D);
+    pack_meta_kernel<<<ns, 1024, meta_smem, st>>>((unsigned char*)pack, s0, K, D, margin_scale);
     RVQ_LAUNCH_CHECK("pack_meta_kernel");
   }
   return RVQ_OK;

@@ -18,9 +18,9 @@
 // when exactly one batch and one class qualify.  Otherwise the candidates (flagged batches x flagged
 // classes, usually 2..4 codes) are re-scored in fp32 with the reference's formula (core_vq.py:181-189,
 // ties -> lowest index).  Frames outside the fp16 image's validity range take an exact fp32 scan.
-// The update pass runs "lane = dimension": for each frame a half-warp reads the candidate rows of the
-// fp32 table (coalesced 512-byte rows, prefetched one frame ahead), re-scores if needed, updates the
-// residual exactly (core_vq.py:364 / :348, with the straight-through arithmetic of :309 in training)
+// The update pass runs "lane = dimension": for each frame a quarter-warp reads the winner's (or the
+// candidates') rows of the fp32 table (128-byte segments, all certified rows of a warp in flight at once),
+// re-scores if needed, updates the residual exactly (core_vq.py:364 / :348, with the straight-through arithmetic of :309 in training)
 // and writes the fp16 operand of the next stage.  Score warp q and helper warp q split the 32 frames
 // of TMEM lane quadrant q for that pass.
 #include "rvq_common.cuh"
@@ -36,7 +36,7 @@ constexpr int kRing = 3;                // B ring slots
 constexpr int kKSteps = kTcKPad / 16;   // 9 UMMA K steps of 16
 constexpr int kAccBufs = 4;             // accumulator buffers of kN TMEM columns
 constexpr int kMaxChunks = 8;           // K <= 1024 on this path
-constexpr int kThreadsTc = 96 + 8 * 32;   // 8 frame warps + TMA producer + 2 MMA issuers
+constexpr int kThreadsTc = 12 * 32;        // 8 frame warps + warpgroup {TMA producer, 2 MMA issuers, idle}
 constexpr int kBig = 5;                 // ncnt marker: more than 4 candidates (enumerate the masks)
 constexpr int kFull = 6;                // ncnt marker: exact scan of the whole table
 
@@ -50,16 +50,36 @@ struct SmemLayout {
   static constexpr uint32_t cmask = ncnt + kM * 4;                 // u32 [128] flagged classes
   static constexpr uint32_t bmask = cmask + kM * 4;                // u32 [128] flagged batches
   static constexpr uint32_t xpart = bmask + kM * 4;                // float [4][128] partial |x|^2
-  static constexpr uint32_t bars = xpart + 4 * kM * 4;
+  static constexpr uint32_t slowq = xpart + 4 * kM * 4;            // u8 [2][128]: frames with 2..4 listed candidates (per stage parity)
+  static constexpr uint32_t wideq = slowq + 2 * kM;                // u8 [2][128]: frames with a wide candidate set
+  static constexpr uint32_t qcnt = wideq + 2 * kM;                 // int [2][2]: queue lengths {slow, wide} per stage parity
+  static constexpr uint32_t bars = qcnt + 16;
   static constexpr uint32_t total = bars + 256;
 };
 struct Bars {
   uint64_t full[kRing], empty[kRing], acc_full[kAccBufs], acc_empty[kAccBufs], a_ready;
+  long long t0;          // kernel start (debug trace)
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 static_assert(SmemLayout::total <= 227 * 1024, "shared memory budget");
 static_assert(kKSteps == 9 && kN == 128, "operand geometry");
+
+// debug timeline of CTA 0 (first tile, first kTraceStages stages): g_trace[stage][warp][event] = cycles since kernel start
+constexpr int kTraceStages = 4, kTraceEv = 16;
+__device__ long long g_trace[kTraceStages * 11 * kTraceEv];
+#ifdef RVQ_TC_TRACE
+#define RVQ_TRACE(stage, ev) do { if (blockIdx.x == 0 && t_tile == 0 && (stage) < kTraceStages && lane == 0) \
+    g_trace[((stage) * 11 + warp) * kTraceEv + (ev)] = clock64() - t_kernel0; } while (0)
+#else
+#define RVQ_TRACE(stage, ev) do { (void)t_tile; } while (0)
+#endif
+// phase timers of the score warps / MMA issuer (rvq_search_stats); they live in registers only when enabled
+#ifdef RVQ_TC_TIMERS
+#define RVQ_TICK(acc) do { const unsigned tt_ = (unsigned)clock(); acc += tt_ - tc0; tc0 = tt_; } while (0)
+#else
+#define RVQ_TICK(acc) do { } while (0)
+#endif
 
 struct TcParams {
   const unsigned char* pack; int K;
@@ -169,128 +189,221 @@ __device__ __noinline__ void resolve_big(unsigned char* smem, int f, int lane, i
   __syncwarp();
 }
 
-// Residual update of frame f by a half-warp (lane g owns dims 4g..4g+3 and 64+4g..64+4g+3): exact fp32
-// r <- r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training), fp16 operand of the
-// next stage, code store, squared-error partial.
-__device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem, int f, int g, float4 r0, float4 r1,
-                                          float4 q0, float4 q1, int code, int s, int64_t tile_n0, float& sq_acc) {
+// ---- update pass: one frame per QUARTER-warp; lane j (0..7) of the quarter owns the 16-byte chunks
+// j, 8+j, 16+j, 24+j of the frame's 512-byte row (dims 4c..4c+3 of chunk c), so every row access of the
+// quarter is one contiguous 128-byte segment ------------------------------------------------------------
+struct Row4 { float4 v[4]; };
+
+__device__ __forceinline__ float quarter_sum(float v) {
+  #pragma unroll
+  for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ Row4 load_row(const float* __restrict__ t32, int code, int j) {
+  const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(code) * 128);
+  Row4 r;
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = __ldg(rp + 8 * i + j);
+  return r;
+}
+__device__ __forceinline__ Row4 load_res(const float* rs, int f, int j) {
+  Row4 r;
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const float4*>(rs + rs_off(f, 8 * i + j));
+  return r;
+}
+__device__ __forceinline__ float dot_row(const Row4& a, const Row4& b) {
+  return (dot4(a.v[0], b.v[0], 0.f) + dot4(a.v[1], b.v[1], 0.f)) + (dot4(a.v[2], b.v[2], 0.f) + dot4(a.v[3], b.v[3], 0.f));
+}
+// fp16 operand of the next stage: chunk c = dims 4c..4c+3 -> K block c/16, 16-byte group (c%16)/2, half c%2
+__device__ __forceinline__ void store_operand(unsigned char* smem, int f, int j, const Row4& n) {
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = 8 * i + j;
+    *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + (c >> 4) * 16384 + asw_off(f, c & 15)) =
+        make_uint2(pack_half2(n.v[i].x, n.v[i].y), pack_half2(n.v[i].z, n.v[i].w));
+  }
+}
+// exact fp32 r <- r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training), fp16
+// operand of the next stage, code store, squared-error partial
+__device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem, int f, int j, const Row4& r, const Row4& qrow,
+                                          int code, int s, int64_t tile_n0, float& sq_acc) {
   float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
-  if (p.ste) {                                   // core_vq.py:309
-    q0.x = r0.x + (q0.x - r0.x); q0.y = r0.y + (q0.y - r0.y); q0.z = r0.z + (q0.z - r0.z); q0.w = r0.w + (q0.w - r0.w);
-    q1.x = r1.x + (q1.x - r1.x); q1.y = r1.y + (q1.y - r1.y); q1.z = r1.z + (q1.z - r1.z); q1.w = r1.w + (q1.w - r1.w);
+  Row4 n;
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 q = qrow.v[i];
+    const float4 rv = r.v[i];
+    if (p.ste) { q.x = rv.x + (q.x - rv.x); q.y = rv.y + (q.y - rv.y); q.z = rv.z + (q.z - rv.z); q.w = rv.w + (q.w - rv.w); }
+    n.v[i] = make_float4(rv.x - q.x, rv.y - q.y, rv.z - q.z, rv.w - q.w);
+    *reinterpret_cast<float4*>(rs + rs_off(f, 8 * i + j)) = n.v[i];
   }
-  const float4 n0 = make_float4(r0.x - q0.x, r0.y - q0.y, r0.z - q0.z, r0.w - q0.w);
-  const float4 n1 = make_float4(r1.x - q1.x, r1.y - q1.y, r1.z - q1.z, r1.w - q1.w);
-  *reinterpret_cast<float4*>(rs + rs_off(f, g)) = n0;
-  *reinterpret_cast<float4*>(rs + rs_off(f, 16 + g)) = n1;
-  const int64_t n = tile_n0 + f;
-  if (n < p.N) {
-    if (g == 0) p.codes[int64_t(s) * p.N + n] = code;
-    if (p.sqerr != nullptr) sq_acc += dot4(n1, n1, dot4(n0, n0, 0.f));
+  const int64_t nfr = tile_n0 + f;
+  if (nfr < p.N) {
+    if (j == 0) p.codes[int64_t(s) * p.N + nfr] = code;
+    if (p.sqerr != nullptr) sq_acc += dot_row(n, n);
   }
-  const uint32_t ao = asw_off(f, g);
-  *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + ao) = make_uint2(pack_half2(n0.x, n0.y), pack_half2(n0.z, n0.w));
-  *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + 16384 + ao) = make_uint2(pack_half2(n1.x, n1.y), pack_half2(n1.z, n1.w));
+  store_operand(smem, f, j, n);
 }
 
-// Re-score of one frame with up to 4 candidates by a half-warp: exact fp32 distances with the reference's
-// formula (core_vq.py:183-187), lowest index on ties; the winner's row is already in registers, so the
-// frame is updated right here.  `act` = this half-warp has a frame (the shuffles need all lanes).
-__device__ __forceinline__ void resolve_small(const TcParams& p, unsigned char* smem, int f, bool act, int g, int s,
-                                              int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn,
-                                              float& sq_acc) {
-  const float* rs = reinterpret_cast<const float*>(smem + SmemLayout::rs);
-  int c[4] = {-1, -1, -1, -1};
-  float4 row[4][2]; float cnv[4];
-  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-  if (act) {
-    const int4 cd = *reinterpret_cast<const int4*>(smem + SmemLayout::cand + f * 16);
-    c[0] = cd.x; c[1] = cd.y; c[2] = cd.z; c[3] = cd.w;
-    r0 = *reinterpret_cast<const float4*>(rs + rs_off(f, g));
-    r1 = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 + g));
-  }
+// Exact fp32 re-score of up to 4 candidate codes (-1 = none) of the frame whose residual this quarter-warp
+// holds: load4 puts the four rows in flight, score4 computes the distances with the reference's formula
+// (core_vq.py:183-187) and keeps the best (lowest code on ties) and its row.  Every lane of the warp must
+// call score4 (shuffles).
+struct Cand4 { int c[4]; Row4 w[4]; float nrm[4]; };
+__device__ __forceinline__ void load4(Cand4& k, int j, const float* __restrict__ t32, const float* __restrict__ cn) {
   #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    row[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); row[u][1] = row[u][0]; cnv[u] = 0.f;
-    if (c[u] >= 0) {
-      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(c[u]) * 128);
-      row[u][0] = __ldg(rp + g); row[u][1] = __ldg(rp + 16 + g); cnv[u] = __ldg(cn + c[u]);
-    }
-  }
-  const float rr = half_warp_sum(dot4(r1, r1, dot4(r0, r0, 0.f)));
-  float dot[4];
-  #pragma unroll
-  for (int u = 0; u < 4; ++u) dot[u] = dot4(r1, row[u][1], dot4(r0, row[u][0], 0.f));
-  #pragma unroll
-  for (int off = 8; off > 0; off >>= 1) {
+    k.nrm[u] = 0.f;
     #pragma unroll
-    for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], off);
+    for (int i = 0; i < 4; ++i) k.w[u].v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k.c[u] >= 0) { k.w[u] = load_row(t32, k.c[u], j); k.nrm[u] = __ldg(cn + k.c[u]); }
   }
-  float best = inf_f(); int bcode = c[0];
-  float4 q0 = row[0][0], q1 = row[0][1];
+}
+__device__ __forceinline__ void score4(const Cand4& k, const Row4& r, float rr, float& best, int& bcode, Row4& brow) {
+  float d[4];
+  #pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = dot_row(r, k.w[u]);
+  #pragma unroll
+  for (int off = 4; off > 0; off >>= 1) {
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], off);
+  }
   #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const float dist = (rr - 2.f * dot[u]) + cnv[u];
-    if (c[u] >= 0 && (dist < best || (dist == best && c[u] < bcode))) { best = dist; bcode = c[u]; q0 = row[u][0]; q1 = row[u][1]; }
+    const float e = (rr - 2.f * d[u]) + k.nrm[u];
+    if (k.c[u] >= 0 && (e < best || (e == best && k.c[u] < bcode))) { best = e; bcode = k.c[u]; brow = k.w[u]; }
   }
-  if (act) apply_row(p, smem, f, g, r0, r1, q0, q1, bcode, s, tile_n0, sq_acc);
 }
 
-// One frame per half-warp.  FIRST: the residual rows were just loaded from x; only the fp16 operand is produced.
+// A frame whose flagged batches x flagged classes give more than 4 candidates: the whole warp works on it,
+// 16 candidates per step (4 per quarter-warp); the quarter that holds the winner's row updates the frame.
+__device__ __noinline__ void resolve_wide(const TcParams& p, unsigned char* smem, int f, int lane, int s, int rot, int nchunks,
+                                             int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn,
+                                             float& sq_acc) {
+  const float* rs = reinterpret_cast<const float*>(smem + SmemLayout::rs);
+  const int qq = lane >> 3, j = lane & 7;
+  const uint32_t cm = *reinterpret_cast<const uint32_t*>(smem + SmemLayout::cmask + f * 4);
+  const uint32_t bm = *reinterpret_cast<const uint32_t*>(smem + SmemLayout::bmask + f * 4);
+  const int nc = __popc(cm), n = nc * __popc(bm);
+  const Row4 r = load_res(rs, f, j);
+  const float rr = quarter_sum(dot_row(r, r));
+  float best = inf_f(); int bcode = 0x7fffffff; Row4 brow = r;
+  for (int t0 = 0; t0 < n; t0 += 16) {
+    Cand4 k;
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 4 * qq + u;
+      k.c[u] = -1;
+      if (t < n) {
+        const int a = int(__fns(bm, 0, t / nc + 1));       // batch in processing order -> actual batch
+        int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
+        k.c[u] = pc * 128 + (a & 3) * 32 + int(__fns(cm, 0, t % nc + 1));
+      }
+    }
+    load4(k, j, t32, cn);
+    score4(k, r, rr, best, bcode, brow);
+  }
+  // best over the four quarters (candidate codes are distinct, so the winner's quarter is unique)
+  float wb = best; int wc = bcode;
+  #pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, wb, off);
+    const int oc = __shfl_xor_sync(0xffffffffu, wc, off);
+    if (ob < wb || (ob == wb && oc < wc)) { wb = ob; wc = oc; }
+  }
+  bool mine = bcode == wc;
+  if (wc == 0x7fffffff) {                                  // NaN distances only: lowest candidate, like an exact scan would
+    mine = qq == 0;
+    if (mine) { const int c0 = (__ffs(bm) - 1); int pc = (c0 >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
+                bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); brow = load_row(t32, bcode, j); }
+  }
+  if (mine) apply_row(p, smem, f, j, r, brow, bcode, s, tile_n0, sq_acc);
+}
+
+// FIRST: the residual rows were just loaded from x; only the fp16 operand is produced.
+// Otherwise: every warp updates the certified frames among the 16 it owns (quarter qq takes f16 + 4k + qq), and
+// the frames that need a re-score are spread over all 32 quarter-warps of the CTA through the stage's queues, so
+// that no warp is left with several re-scores in a row (the stage ends when the slowest warp is done).
 template <bool FIRST>
 __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* smem, int q, int h, int lane, int s, int rot,
-                                            int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn,
-                                            float& sq_acc, long long& t_mid) {
+                                            int nchunks, int64_t tile_n0, const float* __restrict__ t32,
+                                            const float* __restrict__ cn, float& sq_acc, int qpar) {
   float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
-  const int hw = lane >> 4, g = lane & 15;
-  const int f16 = q * 32 + h * 16;                 // the 16 frames this warp owns
-  const int fb = f16 + hw * 8;                     // the 8 frames this half-warp updates
+  const int qq = lane >> 3, j = lane & 7;
+  const int f16 = q * 32 + h * 16;
   if (FIRST) {
     #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int f = fb + k;
-      const float4 n0 = *reinterpret_cast<const float4*>(rs + rs_off(f, g));
-      const float4 n1 = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 + g));
-      const uint32_t ao = asw_off(f, g);
-      *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + ao) = make_uint2(pack_half2(n0.x, n0.y), pack_half2(n0.z, n0.w));
-      *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + 16384 + ao) = make_uint2(pack_half2(n1.x, n1.y), pack_half2(n1.z, n1.w));
+    for (int k = 0; k < 4; ++k) {
+      const int f = f16 + 4 * k + qq;
+      store_operand(smem, f, j, load_res(rs, f, j));
     }
     return;
   }
+  const int par = qpar;
+  const int* qc = reinterpret_cast<const int*>(smem + SmemLayout::qcnt) + par * 2;
+  const int nslow = qc[0], nwide = qc[1];
+  const unsigned char* slowq = smem + SmemLayout::slowq + par * kM;
+  const unsigned char* wideq = smem + SmemLayout::wideq + par * kM;
+  if (threadIdx.x == 0) { int* nx = reinterpret_cast<int*>(smem + SmemLayout::qcnt) + (par ^ 1) * 2; nx[0] = 0; nx[1] = 0; }
   const int nv = lane < 16 ? *reinterpret_cast<const int*>(smem + SmemLayout::ncnt + (f16 + lane) * 4) : 1;
-  uint32_t big = __ballot_sync(0xffffffffu, nv > 4);
-  const uint32_t slow = __ballot_sync(0xffffffffu, nv > 1);     // bit i = frame f16+i needs a re-score
-  // certified winners: all 8 rows of this half-warp go in flight before anything else
-  int code[8]; float4 qa[8], qb[8];
+  const uint32_t slow = __ballot_sync(0xffffffffu, nv > 1);     // bit i = frame f16+i is in one of the queues
+  // certified winners: the rows of all 4 iterations go in flight before anything else
+  int code[4]; Row4 qrow[4];
   #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    code[k] = *reinterpret_cast<const int*>(smem + SmemLayout::cand + (fb + k) * 16);
-    qa[k] = make_float4(0.f, 0.f, 0.f, 0.f); qb[k] = qa[k];
-    if (!((slow >> (hw * 8 + k)) & 1u)) {
-      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(code[k]) * 128);
-      qa[k] = __ldg(rp + g); qb[k] = __ldg(rp + 16 + g);
+  for (int k = 0; k < 4; ++k) {
+    const int fi = 4 * k + qq;
+    code[k] = *reinterpret_cast<const int*>(smem + SmemLayout::cand + (f16 + fi) * 16);
+    if (!((slow >> fi) & 1u)) qrow[k] = load_row(t32, code[k], j);
+    else { qrow[k].v[0] = qrow[k].v[1] = qrow[k].v[2] = qrow[k].v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  }
+  // first re-score item of this quarter-warp: candidate rows in flight while the certified frames are updated
+  const int gq = (h * 4 + q) * 4 + qq;                            // quarter-warp number in the CTA, 0..31
+  Cand4 k4; int fs = -1;
+  k4.c[0] = k4.c[1] = k4.c[2] = k4.c[3] = -1;
+  if (gq < nslow) {
+    fs = slowq[gq];
+    const int4 cd = *reinterpret_cast<const int4*>(smem + SmemLayout::cand + fs * 16);
+    k4.c[0] = cd.x; k4.c[1] = cd.y; k4.c[2] = cd.z; k4.c[3] = cd.w;
+  }
+  load4(k4, j, t32, cn);
+  #pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int fi = 4 * k + qq;
+    if (!((slow >> fi) & 1u)) {
+      const int f = f16 + fi;
+      apply_row(p, smem, f, j, load_res(rs, f, j), qrow[0], code[0], s, tile_n0, sq_acc);
+    }
+    qrow[0] = qrow[1]; qrow[1] = qrow[2]; qrow[2] = qrow[3];
+    code[0] = code[1]; code[1] = code[2]; code[2] = code[3];
+  }
+  // listed re-scores: item gq now, then gq + 32, ... (more than 32 per stage is rare)
+  for (int base = 0; base < nslow; base += 32) {
+    if (base > 0) {
+      fs = -1; k4.c[0] = k4.c[1] = k4.c[2] = k4.c[3] = -1;
+      if (base + gq < nslow) {
+        fs = slowq[base + gq];
+        const int4 cd = *reinterpret_cast<const int4*>(smem + SmemLayout::cand + fs * 16);
+        k4.c[0] = cd.x; k4.c[1] = cd.y; k4.c[2] = cd.z; k4.c[3] = cd.w;
+      }
+      load4(k4, j, t32, cn);
+    }
+    if (__any_sync(0xffffffffu, fs >= 0)) {
+      Row4 r;
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fs >= 0) r = load_res(rs, fs, j);
+      const float rr = quarter_sum(dot_row(r, r));
+      float best = inf_f(); int bcode = 0x7fffffff; Row4 brow = r;
+      score4(k4, r, rr, best, bcode, brow);
+      if (fs >= 0) {
+        if (bcode == 0x7fffffff) { bcode = k4.c[0] < 0 ? 0 : k4.c[0]; brow = load_row(t32, bcode, j); }   // NaN distances
+        apply_row(p, smem, fs, j, r, brow, bcode, s, tile_n0, sq_acc);
+      }
     }
   }
-  while (big) {                                      // wide candidate sets / exact scans -> a single winner
-    const int i = __ffs(big) - 1; big &= big - 1;
-    resolve_big(smem, f16 + i, lane, p.K, rot, t32, cn);
-  }
-  uint32_t todo = slow;                              // re-score + update, two frames per round
-  while (todo) {
-    const int i0 = __ffs(todo) - 1; todo &= todo - 1;
-    const int i1 = __ffs(todo) - 1; if (todo) todo &= todo - 1;
-    const int mine = hw == 0 ? i0 : i1;
-    resolve_small(p, smem, f16 + (mine < 0 ? 0 : mine), mine >= 0, g, s, tile_n0, t32, cn, sq_acc);
-  }
-  t_mid = clock64();
-  #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if ((slow >> (hw * 8 + k)) & 1u) continue;
-    const int f = fb + k;
-    const float4 r0 = *reinterpret_cast<const float4*>(rs + rs_off(f, g));
-    const float4 r1 = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 + g));
-    apply_row(p, smem, f, g, r0, r1, qa[k], qb[k], code[k], s, tile_n0, sq_acc);
-  }
+  // wide candidate sets: one frame per warp at a time
+  for (int i = h * 4 + q; i < nwide; i += 8) resolve_wide(p, smem, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn, sq_acc);
 }
 
 }  // namespace
@@ -315,6 +428,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     ptx::mbar_init(ptx::smem_u32(&bars->a_ready), 8);
     ptx::fence_mbar_init();
   }
+  if (threadIdx.x < 4) reinterpret_cast<int*>(smem + SmemLayout::qcnt)[threadIdx.x] = 0;
   // constant augmented K block of A: k-group 0 = (1, 1, 0, ...) picks up hi/lo of |c|^2, k-group 1 = 0
   for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
     *reinterpret_cast<uint4*>(smem + SmemLayout::a_aug + i * 16) = make_uint4(i < 128 ? pack_half2(1.f, 1.f) : 0u, 0u, 0u, 0u);
@@ -327,7 +441,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  if (threadIdx.x == 0) bars->t0 = clock64();
+  __syncthreads();
+  const long long t_kernel0 = bars->t0;
 
+  // register budget: the two frame warpgroups take what the producer / issuer warpgroup gives up
+  if (warp >= 8) {
+  ptx::reg_dec<72>();
   if (warp == 8) {
     // ===== TMA producer: the chunk stream (stage-major) of every tile =====
     if (lane == 0) {
@@ -335,6 +455,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       for (int64_t t = 0; t < tcnt; ++t) {
         for (int s = 0; s < p.n_q; ++s) {
           const unsigned char* img = pv.tc(p.stage0 + s);
+#ifdef RVQ_TC_TMA_AFTER_A
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), uint32_t(t * p.n_q + s) & 1);   // experiment: no prefetch during the update pass
+#endif
           for (int c = 0; c < nchunks; ++c, ++it) {
             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), ph ^ 1);
@@ -347,7 +470,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       }
     }
     __syncwarp();
-  } else if (warp >= 9) {
+  } else if (warp <= 10) {
     // ===== MMA issuers: descriptors hoisted, 9 MMAs + 2 commits per 128-code chunk.  The issue path of one
     // thread (two barrier waits of ~100 cycles each + the scalar code around every tcgen05.mma) is longer than
     // the 576 tensor cycles of a chunk, so two warps alternate chunks (even / odd). =====
@@ -362,20 +485,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       const uint64_t bd0 = ptx::umma_desc_kmajor_noswz(sbase + SmemLayout::b, kTcLBO, kTcSBO);
       const uint32_t total = uint32_t(tcnt) * uint32_t(p.n_q) * uint32_t(nchunks);
       uint32_t seen = 0xffffffffu;          // last (tile, stage) index whose operand this thread waited for
-      long long w_a = 0, w_bar = 0, w_issue = 0, tm0 = clock64();
-      const long long tm_begin = tm0;
       for (uint32_t it = who; it < total; it += stride) {
         const uint32_t ar = it / uint32_t(nchunks);
         if (ar != seen) {
           ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), ar & 1);                 // fp16 residual operand written
           seen = ar;
-          { const long long tt = clock64(); w_a += tt - tm0; tm0 = tt; }
+          { const int t_tile = int(ar / uint32_t(p.n_q)); RVQ_TRACE(int(ar % uint32_t(p.n_q)), 0); }
         }
         const uint32_t slot = it % kRing, buf = it % kAccBufs;
         ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), (it / kRing) & 1);              // codebook chunk landed
         ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), ((it / kAccBufs) & 1) ^ 1); // accumulator drained
         ptx::tc_fence_after();
-        { const long long tt = clock64(); w_bar += tt - tm0; tm0 = tt; }
         const uint32_t d_tmem = tmem + buf * kN;
         const uint64_t b0 = bd0 + uint64_t((slot * kTcChunkBytes) >> 4);
         #pragma unroll
@@ -383,16 +503,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           ptx::umma_f16_ss(d_tmem, ad[k], b0 + uint64_t((k * 2 * kTcLBO) >> 4), idesc, k > 0 ? 1u : 0u);
         ptx::umma_commit(ptx::smem_u32(&bars->acc_full[buf]));     // scores ready for the score warps
         ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));       // ring slot reusable once read
-        { const long long tt = clock64(); w_issue += tt - tm0; tm0 = tt; }
-      }
-      if (p.counters != nullptr && who == 0) {
-        atomicAdd(&p.counters[11], (unsigned long long)w_a); atomicAdd(&p.counters[12], (unsigned long long)w_bar);
-        atomicAdd(&p.counters[13], 0ull); atomicAdd(&p.counters[14], (unsigned long long)(clock64() - tm_begin));
-        atomicAdd(&p.counters[19], (unsigned long long)w_issue);
+        { const int t_tile = int(ar / uint32_t(p.n_q)); RVQ_TRACE(int(ar % uint32_t(p.n_q)), 1 + int(it % uint32_t(nchunks))); }
       }
     }
     __syncwarp();
+  }   // warp 11 idles: it only completes the third warpgroup (setmaxnreg is per warpgroup)
   } else {
+    ptx::reg_inc<208>();
     // ===== frame warps =====
     const int q = warp & 3;                    // TMEM lane quadrant = frames 32q..32q+31 of the tile
     const int h = warp >= 4 ? 1 : 0;           // 0 = score warp, 1 = helper warp
@@ -402,13 +519,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
     float* xpart = reinterpret_cast<float*>(smem + SmemLayout::xpart);
     const uint32_t bar_a = ptx::smem_u32(&bars->a_ready);
-    unsigned long long n_cert = 0, n_resc = 0, n_full = 0, n_all = 0;
-    long long t_wait = 0, t_epi = 0, t_win = 0, t_upd = 0, t_load = 0, t_res = 0, t_bar = 0;   // phase cycles (lane 0 of each score warp)
+    uint32_t n_cert = 0, n_resc = 0, n_full = 0;                        // search statistics (rvq_search_stats)
+#ifdef RVQ_TC_TIMERS
+    uint32_t t_wait = 0, t_epi = 0, t_win = 0, t_upd = 0, t_load = 0;  // phase cycles (lane 0 of each score warp)
     const long long t_begin = clock64();
+#endif
     uint32_t acc_it = 0;
     for (int64_t t = 0; t < tcnt; ++t) {
       const int64_t tile_n0 = (tile0 + t) * kM;
-      long long tc0 = clock64();
+      const int t_tile = int(t);
+#ifdef RVQ_TC_TIMERS
+      unsigned tc0 = (unsigned)clock();
+#endif
       // ---- load the latent tile: this warp takes dims 64h..64h+63 of its quadrant's 32 frames ----
       {
         const int64_t n = tile_n0 + f;
@@ -433,17 +555,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       ptx::named_bar_sync(pair_bar, 64);
       float xx = ((xpart[f] + xpart[kM + f]) + xpart[2 * kM + f]) + xpart[3 * kM + f];   // exact path's order
       float sq_dummy = 0.f;
-      long long t_mid = 0;
-      update_pass<true>(p, smem, q, h, lane, 0, rot, tile_n0, nullptr, nullptr, sq_dummy, t_mid);
+      update_pass<true>(p, smem, q, h, lane, 0, rot, nchunks, tile_n0, nullptr, nullptr, sq_dummy, 0);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_a);
-      { const long long tt = clock64(); t_load += tt - tc0; tc0 = tt; }
+      RVQ_TICK(t_load);
 
       for (int s = 0; s < p.n_q; ++s) {
         const int st = p.stage0 + s;
         const float* t32 = pv.tab32(st);
         const float* cn = pv.cnorm(st);
+        const int qpar = int((t * p.n_q + s) & 1);          // parity of the re-score queues of this (tile, stage)
+        RVQ_TRACE(s, 0);
         if (h == 0) {
           // ---- scores: per-class and per-batch minima of the K approximate scores of this frame ----
           const StageMeta* meta = pv.meta(st);
@@ -453,36 +576,40 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           float cm[32], bmin[32];
           #pragma unroll
           for (int j = 0; j < 32; ++j) { cm[j] = inf_f(); bmin[j] = inf_f(); }
-          #pragma unroll
-          for (int c = 0; c < kMaxChunks; ++c) {
-            if (c < nchunks) {
-              const uint32_t buf = acc_it % kAccBufs, aph = (acc_it / kAccBufs) & 1;
-              ++acc_it;
-              ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), aph);
-              ptx::tc_fence_after();
-              { const long long tt = clock64(); t_wait += tt - tc0; tc0 = tt; }
-              uint32_t v0[32], v1[32];
-              ptx::tmem_ld32(tlane + buf * kN, v0);
-              ptx::tmem_ld32(tlane + buf * kN + 32, v1);
-              ptx::tmem_ld_wait();
-              #pragma unroll
-              for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
-              bmin[c * 4 + 0] = min32(v0);
-              bmin[c * 4 + 1] = min32(v1);
-              ptx::tmem_ld32(tlane + buf * kN + 64, v0);
-              ptx::tmem_ld32(tlane + buf * kN + 96, v1);
-              ptx::tmem_ld_wait();
-              // scores are in registers: hand the accumulator back before reducing them
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));
-              #pragma unroll
-              for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
-              bmin[c * 4 + 2] = min32(v0);
-              bmin[c * 4 + 3] = min32(v1);
-              { const long long tt = clock64(); t_epi += tt - tc0; tc0 = tt; }
-            }
+          // one rolled iteration per 128-code chunk (the hot loops of a stage must stay inside the instruction cache);
+          // bmin is a shift register: after the loop the a-th batch in processing order sits at 32 - 4*nchunks + a
+          #pragma unroll 1
+          for (int c = 0; c < nchunks; ++c) {
+            const uint32_t buf = acc_it % kAccBufs, aph = (acc_it / kAccBufs) & 1;
+            ++acc_it;
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), aph);
+            ptx::tc_fence_after();
+            RVQ_TICK(t_wait);
+            RVQ_TRACE(s, 1 + c);
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld32(tlane + buf * kN, v0);
+            ptx::tmem_ld32(tlane + buf * kN + 32, v1);
+            #pragma unroll
+            for (int j = 0; j < 28; ++j) bmin[j] = bmin[j + 4];
+            ptx::tmem_ld_wait();
+            #pragma unroll
+            for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+            bmin[28] = min32(v0);
+            bmin[29] = min32(v1);
+            ptx::tmem_ld32(tlane + buf * kN + 64, v0);
+            ptx::tmem_ld32(tlane + buf * kN + 96, v1);
+            ptx::tmem_ld_wait();
+            // scores are in registers: hand the accumulator back before reducing them
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));
+            #pragma unroll
+            for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+            bmin[30] = min32(v0);
+            bmin[31] = min32(v1);
+            RVQ_TICK(t_epi);
           }
+          RVQ_TRACE(s, 9);
           // ---- candidates: certified winner / up to 4 codes to re-score / mask enumeration / exact scan ----
           float m4[4];
           #pragma unroll
@@ -500,7 +627,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
             cm4[j & 3] |= (cm[j] <= thr) ? (1u << j) : 0u;
             bm4[j & 3] |= (bmin[j] <= thr) ? (1u << j) : 0u;
           }
-          const uint32_t cmask = (cm4[0] | cm4[1]) | (cm4[2] | cm4[3]), bmask = (bm4[0] | bm4[1]) | (bm4[2] | bm4[3]);
+          const uint32_t cmask = (cm4[0] | cm4[1]) | (cm4[2] | cm4[3]);
+          const uint32_t bmask = ((bm4[0] | bm4[1]) | (bm4[2] | bm4[3])) >> (32 - 4 * nchunks);   // bit a = a-th batch processed
           const int nc = __popc(cmask), nb = __popc(bmask);
           const bool full = outl || cmask == 0u || bmask == 0u;     // masks are empty only for NaN scores
           const int ncand = nc * nb;
@@ -527,19 +655,41 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           *reinterpret_cast<int*>(smem + SmemLayout::ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
           *reinterpret_cast<uint32_t*>(smem + SmemLayout::cmask + f * 4) = cmask;
           *reinterpret_cast<uint32_t*>(smem + SmemLayout::bmask + f * 4) = bmask;
-          ++n_all;
-          if (full) ++n_full; else if (ncand == 1) ++n_cert; else ++n_resc;
+          {
+            int* qc = reinterpret_cast<int*>(smem + SmemLayout::qcnt) + qpar * 2;
+            if (!full && ncand > 1) {
+              if (ncand <= 4) smem[SmemLayout::slowq + qpar * kM + atomicAdd(&qc[0], 1)] = (unsigned char)f;
+              else            smem[SmemLayout::wideq + qpar * kM + atomicAdd(&qc[1], 1)] = (unsigned char)f;
+            }
+            // frames outside the fp16 image's validity range (or NaN): exact scan right here, then they are certified
+            uint32_t fm = __ballot_sync(0xffffffffu, full);
+            if (fm) __syncwarp();                     // the lanes' ncnt / mask entries are read by the whole warp below
+            while (fm) {
+              const int i = __ffs(fm) - 1; fm &= fm - 1;
+              resolve_big(smem, q * 32 + i, lane, p.K, rot, t32, cn);
+            }
+          }
+          n_full += full ? 1u : 0u; n_cert += (!full && ncand == 1) ? 1u : 0u; n_resc += (!full && ncand > 1) ? 1u : 0u;
           // upper bound of the next residual's |r|^2 (only the margin and the validity test use it):
           // the winner's approximate score is <= m + delta and off by <= delta/2
           if (full) { const float g2 = xnorm + meta->cmax_all; xx = g2 * g2; }
           else xx = fmaxf(xx + m + 1.5f * delta, 0.f) * 1.00001f + 1e-30f;
         }
-        { const long long tt = clock64(); t_win += tt - tc0; tc0 = tt; }
-        ptx::named_bar_sync(pair_bar, 64);       // candidate lists visible to both warps of the quadrant
-        { const long long tt = clock64(); t_bar += tt - tc0; tc0 = tt; }
+        RVQ_TICK(t_win);
+        RVQ_TRACE(s, 10);
+        ptx::named_bar_sync(5, 256);             // candidate lists and re-score queues visible to all 8 frame warps
+        RVQ_TRACE(s, 11);
+#ifdef RVQ_TC_TRACE
+        if (blockIdx.x == 0 && t_tile == 0 && s < kTraceStages && lane == 0) {     // probe: latency of one dependent table load
+          const long long ta = clock64();
+          const float pv0 = __ldg(t32 + size_t((s * 37 + warp * 5 + 3) % p.K) * 128 + 64);
+          const long long tb = clock64() + (pv0 == 123.456f ? 1 : 0);
+          g_trace[(s * 11 + warp) * kTraceEv + 15] = tb - ta;
+        }
+#endif
         float sq = 0.f;
-        update_pass<false>(p, smem, q, h, lane, s, rot, tile_n0, t32, cn, sq, t_mid);
-        t_res += t_mid - tc0;
+        update_pass<false>(p, smem, q, h, lane, s, rot, nchunks, tile_n0, t32, cn, sq, qpar);
+        RVQ_TRACE(s, 13);
         if (s + 1 < p.n_q) {
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -549,8 +699,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           sq = warp_sum(sq);
           if (lane == 0) atomicAdd(&p.sqerr[s], (double)sq);
         }
-        { const long long tt = clock64(); t_upd += tt - tc0; tc0 = tt; }
+        RVQ_TICK(t_upd);
       }
+      ptx::named_bar_sync(5, 256);               // every frame of the tile has its final residual (re-scores run on any warp)
       if (p.residual_out != nullptr) {
         // each warp writes the 16 frames it owns, 512 contiguous bytes per frame
         for (int i = 0; i < 16; ++i) {
@@ -561,23 +712,23 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       }
       ptx::named_bar_sync(pair_bar, 64);         // both warps are done with this tile's rows
     }
-    // search statistics and phase cycles (evidence; see rvq_search_stats)
-    if (h == 0) {
+    // search statistics (evidence; see rvq_search_stats)
+    if (h == 0 && p.counters != nullptr) {
       #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
-        n_all += __shfl_xor_sync(0xffffffffu, n_all, off);
         n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
         n_resc += __shfl_xor_sync(0xffffffffu, n_resc, off);
         n_full += __shfl_xor_sync(0xffffffffu, n_full, off);
       }
-      if (lane == 0 && p.counters != nullptr) {
-        atomicAdd(&p.counters[0], n_all); atomicAdd(&p.counters[1], n_cert);
-        atomicAdd(&p.counters[2], n_resc); atomicAdd(&p.counters[3], n_full);
+      if (lane == 0) {
+        atomicAdd(&p.counters[0], (unsigned long long)(n_cert + n_resc + n_full)); atomicAdd(&p.counters[1], (unsigned long long)n_cert);
+        atomicAdd(&p.counters[2], (unsigned long long)n_resc); atomicAdd(&p.counters[3], (unsigned long long)n_full);
+#ifdef RVQ_TC_TIMERS
         atomicAdd(&p.counters[4], (unsigned long long)t_wait); atomicAdd(&p.counters[5], (unsigned long long)t_epi);
         atomicAdd(&p.counters[6], (unsigned long long)t_win);  atomicAdd(&p.counters[7], (unsigned long long)t_upd);
         atomicAdd(&p.counters[8], (unsigned long long)t_load); atomicAdd(&p.counters[9], (unsigned long long)(clock64() - t_begin));
         atomicAdd(&p.counters[10], 1ull);
-        atomicAdd(&p.counters[15], (unsigned long long)t_res); atomicAdd(&p.counters[16], (unsigned long long)t_bar);
+#endif
       }
     }
   }
@@ -585,6 +736,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 9) ptx::tmem_dealloc(tmem, 512);
+}
+
+int tc_debug_trace(long long* out_host, int n) {
+  const int m = n < kTraceStages * 11 * kTraceEv ? n : kTraceStages * 11 * kTraceEv;
+  RVQ_CUDA(cudaMemcpyFromSymbol(out_host, g_trace, size_t(m) * sizeof(long long)));
+  return m;
 }
 
 int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa, int64_t N, int T, int stage0, int n_q,
