@@ -33,8 +33,10 @@ constexpr int kTcLBO = kTcChunkCodes * 16;         // 2048
 constexpr int kTcSBO = 128;
 
 struct StageMeta {
-  // Two-sided bound on the fp16 tensor-core score error of a frame with norm |x| against any live
-  // code:  |S_k - s_k| <= delta/2,  delta = margin_coef * (|x| + eps1) + margin_abs.
+  // Two-sided bound on the fp16 tensor-core score error of a frame against any live code:
+  //   |S_k - s_k| <= delta/2,  delta = margin_coef * |r| + margin_dr * |r - fp16(r)| + margin_abs
+  // (|r| may be an upper bound; |r - fp16(r)| is the exact rounding residue of the frame's fp16 operand;
+  //  margin_coef covers the rounding of the codes: 2 max_k |(-2c_k) - fp16(-2c_k)|, margin_dr = 2 (2 cref + that)).
   float margin_coef;
   float margin_abs;
   float xlimit;        // frames with |x| >= xlimit take the exact path (outlier codes / fp16 range)
@@ -42,7 +44,7 @@ struct StageMeta {
   float cmin;          // smallest code norm
   int   n_outliers;    // codes excluded from the fp16 image (provably non-winning under xlimit)
   float cmax_all;      // largest norm among ALL codes (bounds the residual growth of exact-path frames)
-  int   reserved;
+  float margin_dr;
 };
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }

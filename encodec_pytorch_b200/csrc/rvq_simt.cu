@@ -44,8 +44,8 @@ __global__ void pack_copy_kernel(PtrTable32 src, unsigned char* pack, int stage_
 // one block per stage: |c|^2, norm statistics, margin metadata and the fp16 UMMA image
 // |score error| <= beta*|x|*|c|: fp16 rounding of x and of -2c (2 * 2^-11 * 2|x||c| by Cauchy-Schwarz)
 // plus slack (x1.125) for the tensor core's fp32 accumulation of 144 products
-constexpr float kBetaFp16   = 4.5f * 4.8828125e-4f;
-constexpr float kEps1       = 1e-3f;                 // absolute slack for fp16 subnormals
+constexpr float kMarginSlack = 1.0625f;              // fp32 accumulation of the 144 products, fp32 norm arithmetic
+constexpr float kHalfUlp     = 4.8828125e-4f;        // 2^-11: relative rounding error bound of fp16
 constexpr float kOutlierMul = 64.f;                  // codes with |c| > 64 * median are outliers
 constexpr float kBigScore   = 60000.f;               // fp16-representable score of an outlier code
 constexpr float kHalfSafe   = 3.0e4f;                // |2c| elements and |c|^2 must stay below fp16 max
@@ -91,26 +91,35 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       __syncthreads();
     }
   }
-  __shared__ float s_thr, s_cref, s_cmin, s_outmin, s_cmax;
+  __shared__ float s_thr, s_cref, s_cmin, s_outmin, s_cmax, s_db2;
   __shared__ int s_nout;
   if (threadIdx.x == 0) {
     float med = norms[K / 2];
     s_thr = kOutlierMul * med;
     s_cmin = norms[0];
     s_cmax = norms[K - 1];
-    s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0;
+    s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0; s_db2 = 0.f;
   }
   __syncthreads();
   // classify (a code is an outlier by norm ratio or by fp16 range); reduce cref / min outlier norm
   {
-    float lcref = 0.f, loutmin = __int_as_float(0x7f800000); int lnout = 0;
+    float lcref = 0.f, loutmin = __int_as_float(0x7f800000), ldb2 = 0.f; int lnout = 0;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       float nv = sqrtf(cn[k]);
       bool o = outl[k] || !(nv <= s_thr);
       outl[k] = o ? 1 : 0;
-      if (o) { loutmin = fminf(loutmin, nv); ++lnout; } else lcref = fmaxf(lcref, nv);
+      if (o) { loutmin = fminf(loutmin, nv); ++lnout; }
+      else {
+        lcref = fmaxf(lcref, nv);
+        // exact rounding residue of this code's fp16 operand row (-2c): |b - fp16(b)|^2
+        const float* row = t32 + size_t(k) * D;
+        float e2 = 0.f;
+        for (int d = 0; d < D; ++d) { const float b = -2.f * row[d]; const float e = b - __half2float(__float2half_rn(b)); e2 = fmaf(e, e, e2); }
+        ldb2 = fmaxf(ldb2, e2);
+      }
     }
     atomicMax((int*)&s_cref, __float_as_int(lcref));          // non-negative floats order as ints
+    atomicMax((int*)&s_db2, __float_as_int(ldb2));
     atomicMin((int*)&s_outmin, __float_as_int(loutmin));
     atomicAdd(&s_nout, lnout);
   }
@@ -118,8 +127,12 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   if (threadIdx.x == 0) {
     StageMeta m;
     m.cref = s_cref; m.cmin = s_cmin; m.n_outliers = s_nout;
-    m.cmax_all = s_cmax; m.reserved = 0;
-    m.margin_coef = margin_scale * 2.f * kBetaFp16 * (s_cref + kEps1);
+    m.cmax_all = s_cmax;
+    // score error of code k for a frame r with fp16 image r~ = r - dr, operand row b_k = fp16(-2 c_k) = -2 c_k - db_k:
+    //   sum_d (r~_d b_kd + 2 r_d c_kd) = -r.db_k + 2 c_k.dr + dr.db_k   =>   |.| <= |r| dbmax + (2 cref + dbmax) |dr|
+    const float dbmax = sqrtf(s_db2) * 1.0001f;
+    m.margin_coef = margin_scale * 2.f * kMarginSlack * dbmax;
+    m.margin_dr = margin_scale * 2.f * kMarginSlack * (2.f * s_cref + dbmax);
     // |c|^2 is carried as fp16 hi + fp16 lo: error <= 2^-22 |c|^2 (+ 2^-24 when lo is subnormal)
     m.margin_abs = 2.f * (2.4e-7f * s_cref * s_cref + 6e-8f);
     // |x| bound under which (a) outlier codes provably lose to the smallest-norm code and
@@ -127,7 +140,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     float xl = 6.0e4f;
     if (s_nout > 0) {
       xl = fminf(xl, 0.5f * (s_outmin - s_cmin));
-      float denom = 2.f * s_cmin + m.margin_coef + 1e-30f;
+      float denom = 2.f * s_cmin + (m.margin_coef + m.margin_dr * kHalfUlp * 1.01f) + 1e-30f;   // |dr| <= 2^-11 |r| (+ subnormals)
       xl = fminf(xl, (0.9f * kBigScore - s_cmin * s_cmin) / denom);
     }
     if (s_nout >= K) xl = 0.f;

@@ -50,7 +50,8 @@ struct SmemLayout {
   static constexpr uint32_t cmask = ncnt + kM * 4;                 // u32 [128] flagged classes
   static constexpr uint32_t bmask = cmask + kM * 4;                // u32 [128] flagged batches
   static constexpr uint32_t xpart = bmask + kM * 4;                // float [4][128] partial |x|^2
-  static constexpr uint32_t slowq = xpart + 4 * kM * 4;            // u8 [2][128]: frames with 2..4 listed candidates (per stage parity)
+  static constexpr uint32_t dr2 = xpart + 4 * kM * 4;              // float [128]: |r - fp16(r)|^2 of every frame's current operand
+  static constexpr uint32_t slowq = dr2 + kM * 4;            // u8 [2][128]: frames with 2..4 listed candidates (per stage parity)
   static constexpr uint32_t wideq = slowq + 2 * kM;                // u8 [2][128]: frames with a wide candidate set
   static constexpr uint32_t qcnt = wideq + 2 * kM;                 // int [2][2]: queue lengths {slow, wide} per stage parity
   static constexpr uint32_t bars = qcnt + 16;
@@ -215,18 +216,29 @@ __device__ __forceinline__ Row4 load_res(const float* rs, int f, int j) {
 __device__ __forceinline__ float dot_row(const Row4& a, const Row4& b) {
   return (dot4(a.v[0], b.v[0], 0.f) + dot4(a.v[1], b.v[1], 0.f)) + (dot4(a.v[2], b.v[2], 0.f) + dot4(a.v[3], b.v[3], 0.f));
 }
-// fp16 operand of the next stage: chunk c = dims 4c..4c+3 -> K block c/16, 16-byte group (c%16)/2, half c%2
-__device__ __forceinline__ void store_operand(unsigned char* smem, int f, int j, const Row4& n) {
+// fp16 operand of the next stage: chunk c = dims 4c..4c+3 -> K block c/16, 16-byte group (c%16)/2, half c%2.
+// Also records the exact squared rounding residue |r - fp16(r)|^2 of the frame (it enters the score-error
+// margin of the next stage).  Called by whole quarter-warps (8 converged lanes).
+__device__ __forceinline__ void store_operand(unsigned char* smem, int f, int j, int qq, const Row4& n) {
+  float e2 = 0.f;
   #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = 8 * i + j;
+    const __half2 h0 = __floats2half2_rn(n.v[i].x, n.v[i].y), h1 = __floats2half2_rn(n.v[i].z, n.v[i].w);
     *reinterpret_cast<uint2*>(smem + SmemLayout::a_sw + (c >> 4) * 16384 + asw_off(f, c & 15)) =
-        make_uint2(pack_half2(n.v[i].x, n.v[i].y), pack_half2(n.v[i].z, n.v[i].w));
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+    const float ex = n.v[i].x - b0.x, ey = n.v[i].y - b0.y, ez = n.v[i].z - b1.x, ew = n.v[i].w - b1.y;
+    e2 = fmaf(ex, ex, e2); e2 = fmaf(ey, ey, e2); e2 = fmaf(ez, ez, e2); e2 = fmaf(ew, ew, e2);
   }
+  const uint32_t qmask = 0xffu << (8 * qq);
+  #pragma unroll
+  for (int off = 4; off > 0; off >>= 1) e2 += __shfl_xor_sync(qmask, e2, off);
+  if (j == 0) reinterpret_cast<float*>(smem + SmemLayout::dr2)[f] = e2;
 }
 // exact fp32 r <- r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training), fp16
 // operand of the next stage, code store, squared-error partial
-__device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem, int f, int j, const Row4& r, const Row4& qrow,
+__device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem, int f, int j, int qq, const Row4& r, const Row4& qrow,
                                           int code, int s, int64_t tile_n0, float& sq_acc) {
   float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
   Row4 n;
@@ -243,7 +255,7 @@ __device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem
     if (j == 0) p.codes[int64_t(s) * p.N + nfr] = code;
     if (p.sqerr != nullptr) sq_acc += dot_row(n, n);
   }
-  store_operand(smem, f, j, n);
+  store_operand(smem, f, j, qq, n);
 }
 
 // Exact fp32 re-score of up to 4 candidate codes (-1 = none) of the frame whose residual this quarter-warp
@@ -285,24 +297,32 @@ __device__ __noinline__ void resolve_wide(const TcParams& p, unsigned char* smem
   const int qq = lane >> 3, j = lane & 7;
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(smem + SmemLayout::cmask + f * 4);
   const uint32_t bm = *reinterpret_cast<const uint32_t*>(smem + SmemLayout::bmask + f * 4);
-  const int nc = __popc(cm), n = nc * __popc(bm);
+  const int nc = __popc(cm);
   const Row4 r = load_res(rs, f, j);
   const float rr = quarter_sum(dot_row(r, r));
   float best = inf_f(); int bcode = 0x7fffffff; Row4 brow = r;
-  for (int t0 = 0; t0 < n; t0 += 16) {
-    Cand4 k;
+  // quarter qq takes the flagged batches number qq, qq + 4, ...; within a batch the flagged classes four at a time
+  uint32_t bmq = bm;
+  for (int i = 0; i < qq; ++i) bmq &= bmq - 1;
+  const int nb = __popc(bm);
+  for (int ob = 0; ob < nb; ob += 4) {
+    const int a = bmq ? __ffs(bmq) - 1 : -1;
     #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + 4 * qq + u;
-      k.c[u] = -1;
-      if (t < n) {
-        const int a = int(__fns(bm, 0, t / nc + 1));       // batch in processing order -> actual batch
-        int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
-        k.c[u] = pc * 128 + (a & 3) * 32 + int(__fns(cm, 0, t % nc + 1));
+    for (int i = 0; i < 4; ++i) bmq &= bmq - 1;
+    int base = 0;
+    if (a >= 0) { int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks; base = pc * 128 + (a & 3) * 32; }   // processing order -> code
+    uint32_t cmq = cm;
+    for (int oc = 0; oc < nc; oc += 4) {
+      Cand4 k;
+      #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = cmq ? __ffs(cmq) - 1 : -1;
+        cmq &= cmq - 1;
+        k.c[u] = (a >= 0 && jj >= 0) ? base + jj : -1;
       }
+      load4(k, j, t32, cn);
+      score4(k, r, rr, best, bcode, brow);
     }
-    load4(k, j, t32, cn);
-    score4(k, r, rr, best, bcode, brow);
   }
   // best over the four quarters (candidate codes are distinct, so the winner's quarter is unique)
   float wb = best; int wc = bcode;
@@ -318,11 +338,11 @@ __device__ __noinline__ void resolve_wide(const TcParams& p, unsigned char* smem
     if (mine) { const int c0 = (__ffs(bm) - 1); int pc = (c0 >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
                 bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); brow = load_row(t32, bcode, j); }
   }
-  if (mine) apply_row(p, smem, f, j, r, brow, bcode, s, tile_n0, sq_acc);
+  if (mine) apply_row(p, smem, f, j, qq, r, brow, bcode, s, tile_n0, sq_acc);
 }
 
 // FIRST: the residual rows were just loaded from x; only the fp16 operand is produced.
-// Otherwise: every warp updates the certified frames among the 16 it owns (quarter qq takes f16 + 4k + qq), and
+// Otherwise: every warp updates the certified frames among the 16 it owns (quarter qq takes f16 + 4 qq + k: the four frames of a step then sit in different bank groups of the operand tile), and
 // the frames that need a re-score are spread over all 32 quarter-warps of the CTA through the stage's queues, so
 // that no warp is left with several re-scores in a row (the stage ends when the slowest warp is done).
 template <bool FIRST>
@@ -335,8 +355,8 @@ __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* sm
   if (FIRST) {
     #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int f = f16 + 4 * k + qq;
-      store_operand(smem, f, j, load_res(rs, f, j));
+      const int f = f16 + 4 * qq + k;
+      store_operand(smem, f, j, qq, load_res(rs, f, j));
     }
     return;
   }
@@ -352,11 +372,13 @@ __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* sm
   int code[4]; Row4 qrow[4];
   #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int fi = 4 * k + qq;
+    const int fi = 4 * qq + k;
     code[k] = *reinterpret_cast<const int*>(smem + SmemLayout::cand + (f16 + fi) * 16);
     if (!((slow >> fi) & 1u)) qrow[k] = load_row(t32, code[k], j);
     else { qrow[k].v[0] = qrow[k].v[1] = qrow[k].v[2] = qrow[k].v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
   }
+  // wide candidate sets first (their latency overlaps the certified rows in flight): one frame per warp at a time
+  for (int i = h * 4 + q; i < nwide; i += 8) resolve_wide(p, smem, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn, sq_acc);
   // first re-score item of this quarter-warp: candidate rows in flight while the certified frames are updated
   const int gq = (h * 4 + q) * 4 + qq;                            // quarter-warp number in the CTA, 0..31
   Cand4 k4; int fs = -1;
@@ -369,10 +391,10 @@ __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* sm
   load4(k4, j, t32, cn);
   #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    const int fi = 4 * k + qq;
+    const int fi = 4 * qq + k;
     if (!((slow >> fi) & 1u)) {
       const int f = f16 + fi;
-      apply_row(p, smem, f, j, load_res(rs, f, j), qrow[0], code[0], s, tile_n0, sq_acc);
+      apply_row(p, smem, f, j, qq, load_res(rs, f, j), qrow[0], code[0], s, tile_n0, sq_acc);
     }
     qrow[0] = qrow[1]; qrow[1] = qrow[2]; qrow[2] = qrow[3];
     code[0] = code[1]; code[1] = code[2]; code[2] = code[3];
@@ -398,12 +420,10 @@ __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* sm
       score4(k4, r, rr, best, bcode, brow);
       if (fs >= 0) {
         if (bcode == 0x7fffffff) { bcode = k4.c[0] < 0 ? 0 : k4.c[0]; brow = load_row(t32, bcode, j); }   // NaN distances
-        apply_row(p, smem, fs, j, r, brow, bcode, s, tile_n0, sq_acc);
+        apply_row(p, smem, fs, j, qq, r, brow, bcode, s, tile_n0, sq_acc);
       }
     }
   }
-  // wide candidate sets: one frame per warp at a time
-  for (int i = h * 4 + q; i < nwide; i += 8) resolve_wide(p, smem, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn, sq_acc);
 }
 
 }  // namespace
@@ -571,7 +591,6 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           // ---- scores: per-class and per-batch minima of the K approximate scores of this frame ----
           const StageMeta* meta = pv.meta(st);
           const float xnorm = sqrtf(xx);
-          const float delta = meta->margin_coef * (xnorm + 1e-3f) + meta->margin_abs;
           const bool outl = !(xnorm < meta->xlimit);      // also true for NaN
           float cm[32], bmin[32];
           #pragma unroll
@@ -610,6 +629,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
             RVQ_TICK(t_epi);
           }
           RVQ_TRACE(s, 9);
+          // the rounding residue of this frame's operand was written by whichever warp updated the frame; the scores
+          // above could only exist after every warp had finished that update
+          const float drn = sqrtf(reinterpret_cast<const float*>(smem + SmemLayout::dr2)[f]) * 1.001f;
+          const float delta = meta->margin_coef * xnorm + meta->margin_dr * drn + meta->margin_abs;
           // ---- candidates: certified winner / up to 4 codes to re-score / mask enumeration / exact scan ----
           float m4[4];
           #pragma unroll
