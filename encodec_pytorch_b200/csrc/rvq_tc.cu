@@ -11,7 +11,7 @@
 //   B = fp16 image of the codebook, 128 codes x 144 per chunk (cols 0..127 = -2c, cols 128,129 = hi/lo
 //       of |c|^2), streamed by the TMA engine (cp.async.bulk) from the pre-arranged pack into a ring.
 // Warp roles (320 threads): 0..3 = score warps (thread = TMEM lane = frame), 4..7 = helper warps, 8 = TMA
-// producer, 9 = MMA issuer of the even chunks (+ TMEM alloc), 10 = MMA issuer of the odd chunks.  A score warp reads the accumulators with
+// producer, 9..11 = MMA issuers (chunks round-robin; warp 9 also allocates TMEM).  A score warp reads the accumulators with
 // tcgen05.ld and keeps, per frame, the minimum over every 32-code batch and over every residue class
 // (code mod 32).  A code is within `delta` of the minimum iff its batch AND its class are; delta bounds
 // the fp16 score error two-sidedly (rvq_common.cuh, StageMeta), so the exact fp32 winner is certified
@@ -290,9 +290,9 @@ __device__ __forceinline__ void score4(const Cand4& k, const Row4& r, float rr, 
 
 // A frame whose flagged batches x flagged classes give more than 4 candidates: the whole warp works on it,
 // 16 candidates per step (4 per quarter-warp); the quarter that holds the winner's row updates the frame.
-__device__ __noinline__ void resolve_wide(const TcParams& p, unsigned char* smem, int f, int lane, int s, int rot, int nchunks,
-                                             int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn,
-                                             float& sq_acc) {
+__device__ __noinline__ float resolve_wide(const TcParams& p, unsigned char* smem, int f, int lane, int s, int rot, int nchunks,
+                                              int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn) {
+  float sq_acc = 0.f;
   const float* rs = reinterpret_cast<const float*>(smem + SmemLayout::rs);
   const int qq = lane >> 3, j = lane & 7;
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(smem + SmemLayout::cmask + f * 4);
@@ -339,6 +339,7 @@ __device__ __noinline__ void resolve_wide(const TcParams& p, unsigned char* smem
                 bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); brow = load_row(t32, bcode, j); }
   }
   if (mine) apply_row(p, smem, f, j, qq, r, brow, bcode, s, tile_n0, sq_acc);
+  return sq_acc;
 }
 
 // FIRST: the residual rows were just loaded from x; only the fp16 operand is produced.
@@ -378,7 +379,8 @@ __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* sm
     else { qrow[k].v[0] = qrow[k].v[1] = qrow[k].v[2] = qrow[k].v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
   }
   // wide candidate sets first (their latency overlaps the certified rows in flight): one frame per warp at a time
-  for (int i = h * 4 + q; i < nwide; i += 8) resolve_wide(p, smem, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn, sq_acc);
+  #pragma unroll 1
+  for (int i = h * 4 + q; i < nwide; i += 8) sq_acc += resolve_wide(p, smem, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
   // first re-score item of this quarter-warp: candidate rows in flight while the certified frames are updated
   const int gq = (h * 4 + q) * 4 + qq;                            // quarter-warp number in the CTA, 0..31
   Cand4 k4; int fs = -1;
@@ -490,12 +492,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       }
     }
     __syncwarp();
-  } else if (warp <= 10) {
+  } else {
     // ===== MMA issuers: descriptors hoisted, 9 MMAs + 2 commits per 128-code chunk.  The issue path of one
     // thread (two barrier waits of ~100 cycles each + the scalar code around every tcgen05.mma) is longer than
-    // the 576 tensor cycles of a chunk, so two warps alternate chunks (even / odd). =====
+    // the 576 tensor cycles of a chunk, so three warps take the chunks round-robin. =====
     const uint32_t who = warp - 9;
-    const uint32_t stride = nchunks >= 2 ? 2u : 1u;
+    const uint32_t stride = nchunks >= 3 ? 3u : (nchunks >= 2 ? 2u : 1u);
     if (lane == 0 && who < stride) {
       constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
       uint64_t ad[kKSteps];
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       }
     }
     __syncwarp();
-  }   // warp 11 idles: it only completes the third warpgroup (setmaxnreg is per warpgroup)
+  }
   } else {
     ptx::reg_inc<208>();
     // ===== frame warps =====
