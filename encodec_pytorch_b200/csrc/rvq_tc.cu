@@ -238,6 +238,7 @@ __device__ __forceinline__ void store_operand(unsigned char* smem, int f, int j,
 }
 // exact fp32 r <- r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training), fp16
 // operand of the next stage, code store, squared-error partial
+template <bool TRAIN>
 __device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem, int f, int j, int qq, const Row4& r, const Row4& qrow,
                                           int code, int s, int64_t tile_n0, float& sq_acc) {
   float* rs = reinterpret_cast<float*>(smem + SmemLayout::rs);
@@ -246,14 +247,14 @@ __device__ __forceinline__ void apply_row(const TcParams& p, unsigned char* smem
   for (int i = 0; i < 4; ++i) {
     float4 q = qrow.v[i];
     const float4 rv = r.v[i];
-    if (p.ste) { q.x = rv.x + (q.x - rv.x); q.y = rv.y + (q.y - rv.y); q.z = rv.z + (q.z - rv.z); q.w = rv.w + (q.w - rv.w); }
+    if (TRAIN && p.ste) { q.x = rv.x + (q.x - rv.x); q.y = rv.y + (q.y - rv.y); q.z = rv.z + (q.z - rv.z); q.w = rv.w + (q.w - rv.w); }
     n.v[i] = make_float4(rv.x - q.x, rv.y - q.y, rv.z - q.z, rv.w - q.w);
     *reinterpret_cast<float4*>(rs + rs_off(f, 8 * i + j)) = n.v[i];
   }
   const int64_t nfr = tile_n0 + f;
   if (nfr < p.N) {
     if (j == 0) p.codes[int64_t(s) * p.N + nfr] = code;
-    if (p.sqerr != nullptr) sq_acc += dot_row(n, n);
+    if (TRAIN && p.sqerr != nullptr) sq_acc += dot_row(n, n);
   }
   store_operand(smem, f, j, qq, n);
 }
@@ -267,8 +268,6 @@ __device__ __forceinline__ void load4(Cand4& k, int j, const float* __restrict__
   #pragma unroll
   for (int u = 0; u < 4; ++u) {
     k.nrm[u] = 0.f;
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) k.w[u].v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k.c[u] >= 0) { k.w[u] = load_row(t32, k.c[u], j); k.nrm[u] = __ldg(cn + k.c[u]); }
   }
 }
@@ -290,6 +289,7 @@ __device__ __forceinline__ void score4(const Cand4& k, const Row4& r, float rr, 
 
 // A frame whose flagged batches x flagged classes give more than 4 candidates: the whole warp works on it,
 // 16 candidates per step (4 per quarter-warp); the quarter that holds the winner's row updates the frame.
+template <bool TRAIN>
 __device__ __noinline__ float resolve_wide(const TcParams& p, unsigned char* smem, int f, int lane, int s, int rot, int nchunks,
                                               int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn) {
   float sq_acc = 0.f;
@@ -305,6 +305,7 @@ __device__ __noinline__ float resolve_wide(const TcParams& p, unsigned char* sme
   uint32_t bmq = bm;
   for (int i = 0; i < qq; ++i) bmq &= bmq - 1;
   const int nb = __popc(bm);
+  #pragma unroll 1
   for (int ob = 0; ob < nb; ob += 4) {
     const int a = bmq ? __ffs(bmq) - 1 : -1;
     #pragma unroll
@@ -312,6 +313,7 @@ __device__ __noinline__ float resolve_wide(const TcParams& p, unsigned char* sme
     int base = 0;
     if (a >= 0) { int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks; base = pc * 128 + (a & 3) * 32; }   // processing order -> code
     uint32_t cmq = cm;
+    #pragma unroll 1
     for (int oc = 0; oc < nc; oc += 4) {
       Cand4 k;
       #pragma unroll
@@ -338,15 +340,19 @@ __device__ __noinline__ float resolve_wide(const TcParams& p, unsigned char* sme
     if (mine) { const int c0 = (__ffs(bm) - 1); int pc = (c0 >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
                 bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); brow = load_row(t32, bcode, j); }
   }
-  if (mine) apply_row(p, smem, f, j, qq, r, brow, bcode, s, tile_n0, sq_acc);
+  if (mine) apply_row<TRAIN>(p, smem, f, j, qq, r, brow, bcode, s, tile_n0, sq_acc);
   return sq_acc;
 }
 
 // FIRST: the residual rows were just loaded from x; only the fp16 operand is produced.
-// Otherwise: every warp updates the certified frames among the 16 it owns (quarter qq takes f16 + 4 qq + k: the four frames of a step then sit in different bank groups of the operand tile), and
-// the frames that need a re-score are spread over all 32 quarter-warps of the CTA through the stage's queues, so
-// that no warp is left with several re-scores in a row (the stage ends when the slowest warp is done).
-template <bool FIRST>
+// Otherwise every quarter-warp walks a short list of items: the certified frames among the 4 it owns (frame
+// f16 + 4 qq + k: the four frames of a step then sit in different bank groups of the operand tile), then its
+// share of the stage's re-score queue (items gq, gq + 32, ... -- the frames that need a re-score are spread over
+// all 32 quarter-warps of the CTA, so no warp is left with several of them).  ONE rolled loop body serves both
+// kinds; the first candidate row of the next item is fetched while the current one is processed.  Keeping this
+// code small matters more than hiding every latency: a stage's hot code has to fit the SM's instruction cache
+// (ncu showed a 67 % icc hit rate and a saturated GPC instruction cache with the unrolled version).
+template <bool FIRST, bool TRAIN>
 __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* smem, int q, int h, int lane, int s, int rot,
                                             int nchunks, int64_t tile_n0, const float* __restrict__ t32,
                                             const float* __restrict__ cn, float& sq_acc, int qpar) {
@@ -354,82 +360,79 @@ __device__ __forceinline__ void update_pass(const TcParams& p, unsigned char* sm
   const int qq = lane >> 3, j = lane & 7;
   const int f16 = q * 32 + h * 16;
   if (FIRST) {
-    #pragma unroll
+    #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
       const int f = f16 + 4 * qq + k;
       store_operand(smem, f, j, qq, load_res(rs, f, j));
     }
     return;
   }
-  const int par = qpar;
-  const int* qc = reinterpret_cast<const int*>(smem + SmemLayout::qcnt) + par * 2;
+  const int* qc = reinterpret_cast<const int*>(smem + SmemLayout::qcnt) + qpar * 2;
   const int nslow = qc[0], nwide = qc[1];
-  const unsigned char* slowq = smem + SmemLayout::slowq + par * kM;
-  const unsigned char* wideq = smem + SmemLayout::wideq + par * kM;
-  if (threadIdx.x == 0) { int* nx = reinterpret_cast<int*>(smem + SmemLayout::qcnt) + (par ^ 1) * 2; nx[0] = 0; nx[1] = 0; }
+  const unsigned char* slowq = smem + SmemLayout::slowq + qpar * kM;
+  const unsigned char* wideq = smem + SmemLayout::wideq + qpar * kM;
+  if (threadIdx.x == 0) { int* nx = reinterpret_cast<int*>(smem + SmemLayout::qcnt) + (qpar ^ 1) * 2; nx[0] = 0; nx[1] = 0; }
   const int nv = lane < 16 ? *reinterpret_cast<const int*>(smem + SmemLayout::ncnt + (f16 + lane) * 4) : 1;
   const uint32_t slow = __ballot_sync(0xffffffffu, nv > 1);     // bit i = frame f16+i is in one of the queues
-  // certified winners: the rows of all 4 iterations go in flight before anything else
-  int code[4]; Row4 qrow[4];
-  #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int fi = 4 * qq + k;
-    code[k] = *reinterpret_cast<const int*>(smem + SmemLayout::cand + (f16 + fi) * 16);
-    if (!((slow >> fi) & 1u)) qrow[k] = load_row(t32, code[k], j);
-    else { qrow[k].v[0] = qrow[k].v[1] = qrow[k].v[2] = qrow[k].v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
-  }
-  // wide candidate sets first (their latency overlaps the certified rows in flight): one frame per warp at a time
+  const int gq = (h * 4 + q) * 4 + qq;                          // quarter-warp number in the CTA, 0..31
+  const int nitems = 4 + ((nslow + 31) >> 5);
+  // item it -> frame (or -1) and its candidate list
+  auto fetch = [&](int it, int& f, int4& cd) {
+    if (it < 4) { const int fi = 4 * qq + it; f = ((slow >> fi) & 1u) ? -1 : f16 + fi; }
+    else { const int qi = (it - 4) * 32 + gq; f = qi < nslow ? int(slowq[qi]) : -1; }
+    cd = make_int4(-1, -1, -1, -1);
+    if (f >= 0) cd = *reinterpret_cast<const int4*>(smem + SmemLayout::cand + f * 16);
+  };
+  int fn; int4 cdn; Row4 rown;
+  fetch(0, fn, cdn);
+  if (fn >= 0) rown = load_row(t32, cdn.x, j);
+  // wide candidate sets (their latency overlaps the first row in flight): one frame per warp at a time
   #pragma unroll 1
-  for (int i = h * 4 + q; i < nwide; i += 8) sq_acc += resolve_wide(p, smem, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
-  // first re-score item of this quarter-warp: candidate rows in flight while the certified frames are updated
-  const int gq = (h * 4 + q) * 4 + qq;                            // quarter-warp number in the CTA, 0..31
-  Cand4 k4; int fs = -1;
-  k4.c[0] = k4.c[1] = k4.c[2] = k4.c[3] = -1;
-  if (gq < nslow) {
-    fs = slowq[gq];
-    const int4 cd = *reinterpret_cast<const int4*>(smem + SmemLayout::cand + fs * 16);
-    k4.c[0] = cd.x; k4.c[1] = cd.y; k4.c[2] = cd.z; k4.c[3] = cd.w;
-  }
-  load4(k4, j, t32, cn);
+  for (int i = h * 4 + q; i < nwide; i += 8) sq_acc += resolve_wide<TRAIN>(p, smem, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
   #pragma unroll 1
-  for (int k = 0; k < 4; ++k) {
-    const int fi = 4 * qq + k;
-    if (!((slow >> fi) & 1u)) {
-      const int f = f16 + fi;
-      apply_row(p, smem, f, j, qq, load_res(rs, f, j), qrow[0], code[0], s, tile_n0, sq_acc);
+  for (int it = 0; it < nitems; ++it) {
+    const int f = fn; const int4 cd = cdn;
+    Row4 row = rown;
+    if (it + 1 < nitems) {
+      fetch(it + 1, fn, cdn);
+      if (fn >= 0) rown = load_row(t32, cdn.x, j);
     }
-    qrow[0] = qrow[1]; qrow[1] = qrow[2]; qrow[2] = qrow[3];
-    code[0] = code[1]; code[1] = code[2]; code[2] = code[3];
-  }
-  // listed re-scores: item gq now, then gq + 32, ... (more than 32 per stage is rare)
-  for (int base = 0; base < nslow; base += 32) {
-    if (base > 0) {
-      fs = -1; k4.c[0] = k4.c[1] = k4.c[2] = k4.c[3] = -1;
-      if (base + gq < nslow) {
-        fs = slowq[base + gq];
-        const int4 cd = *reinterpret_cast<const int4*>(smem + SmemLayout::cand + fs * 16);
-        k4.c[0] = cd.x; k4.c[1] = cd.y; k4.c[2] = cd.z; k4.c[3] = cd.w;
-      }
-      load4(k4, j, t32, cn);
-    }
-    if (__any_sync(0xffffffffu, fs >= 0)) {
-      Row4 r;
+    Row4 r;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f >= 0) r = load_res(rs, f, j);
+    int code = cd.x;
+    if (__any_sync(0xffffffffu, cd.y >= 0)) {                    // some quarter has 2..4 candidates: exact fp32 re-score
+      const bool multi = cd.y >= 0;
+      Row4 w1 = row, w2 = row, w3 = row;
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+      if (multi) n0 = __ldg(cn + cd.x);
+      if (cd.y >= 0) { w1 = load_row(t32, cd.y, j); n1 = __ldg(cn + cd.y); }
+      if (cd.z >= 0) { w2 = load_row(t32, cd.z, j); n2 = __ldg(cn + cd.z); }
+      if (cd.w >= 0) { w3 = load_row(t32, cd.w, j); n3 = __ldg(cn + cd.w); }
+      float d0 = dot_row(r, row), d1 = dot_row(r, w1), d2 = dot_row(r, w2), d3 = dot_row(r, w3), rr = dot_row(r, r);
       #pragma unroll
-      for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (fs >= 0) r = load_res(rs, fs, j);
-      const float rr = quarter_sum(dot_row(r, r));
-      float best = inf_f(); int bcode = 0x7fffffff; Row4 brow = r;
-      score4(k4, r, rr, best, bcode, brow);
-      if (fs >= 0) {
-        if (bcode == 0x7fffffff) { bcode = k4.c[0] < 0 ? 0 : k4.c[0]; brow = load_row(t32, bcode, j); }   // NaN distances
-        apply_row(p, smem, fs, j, qq, r, brow, bcode, s, tile_n0, sq_acc);
+      for (int off = 4; off > 0; off >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
+        rr += __shfl_xor_sync(0xffffffffu, rr, off);
+      }
+      if (multi) {                                               // core_vq.py:183-187, lowest index on ties
+        float best = (rr - 2.f * d0) + n0;
+        if (!(best == best)) best = inf_f();                     // NaN distances: keep the first candidate unless a finite one exists
+        const float e1 = (rr - 2.f * d1) + n1, e2 = (rr - 2.f * d2) + n2, e3 = (rr - 2.f * d3) + n3;
+        if (e1 < best || (e1 == best && cd.y < code)) { best = e1; code = cd.y; row = w1; }
+        if (cd.z >= 0 && (e2 < best || (e2 == best && cd.z < code))) { best = e2; code = cd.z; row = w2; }
+        if (cd.w >= 0 && (e3 < best || (e3 == best && cd.w < code))) { best = e3; code = cd.w; row = w3; }
       }
     }
+    if (f >= 0) apply_row<TRAIN>(p, smem, f, j, qq, r, row, code, s, tile_n0, sq_acc);
   }
 }
 
 }  // namespace
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       ptx::named_bar_sync(pair_bar, 64);
       float xx = ((xpart[f] + xpart[kM + f]) + xpart[2 * kM + f]) + xpart[3 * kM + f];   // exact path's order
       float sq_dummy = 0.f;
-      update_pass<true>(p, smem, q, h, lane, 0, rot, nchunks, tile_n0, nullptr, nullptr, sq_dummy, 0);
+      update_pass<true, TRAIN>(p, smem, q, h, lane, 0, rot, nchunks, tile_n0, nullptr, nullptr, sq_dummy, 0);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_a);
@@ -713,21 +716,21 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         }
 #endif
         float sq = 0.f;
-        update_pass<false>(p, smem, q, h, lane, s, rot, nchunks, tile_n0, t32, cn, sq, qpar);
+        update_pass<false, TRAIN>(p, smem, q, h, lane, s, rot, nchunks, tile_n0, t32, cn, sq, qpar);
         RVQ_TRACE(s, 13);
         if (s + 1 < p.n_q) {
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar_a);
         }
-        if (p.sqerr != nullptr) {
+        if (TRAIN && p.sqerr != nullptr) {
           sq = warp_sum(sq);
           if (lane == 0) atomicAdd(&p.sqerr[s], (double)sq);
         }
         RVQ_TICK(t_upd);
       }
       ptx::named_bar_sync(5, 256);               // every frame of the tile has its final residual (re-scores run on any warp)
-      if (p.residual_out != nullptr) {
+      if (TRAIN && p.residual_out != nullptr) {
         // each warp writes the 16 frames it owns, 512 contiguous bytes per frame
         for (int i = 0; i < 16; ++i) {
           const int fo = q * 32 + h * 16 + i;
@@ -781,7 +784,8 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   RVQ_CUDA(cudaGetDevice(&dev));
   if (dev != sm_dev) {
     RVQ_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    RVQ_CUDA(cudaFuncSetAttribute(tc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout::total));
+    RVQ_CUDA(cudaFuncSetAttribute(tc_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout::total));
+    RVQ_CUDA(cudaFuncSetAttribute(tc_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout::total));
     sm_dev = dev;
   }
   PackView pv(a.pack, a.K, a.D);
@@ -795,7 +799,10 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   p.counters = pv.counters();
   const int64_t ntiles = (N + kM - 1) / kM;
   const unsigned grid = unsigned(ntiles < sm_count ? ntiles : sm_count);
-  tc_encode_kernel<<<grid, kThreadsTc, SmemLayout::total, st>>>(p);
+  // the lean variant serves plain encodes; straight-through arithmetic, loss numerators and the residual output
+  // live in the other one (a stage's hot code has to fit the instruction cache)
+  if (p.ste || p.sqerr != nullptr || p.residual_out != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, SmemLayout::total, st>>>(p);
+  else tc_encode_kernel<false><<<grid, kThreadsTc, SmemLayout::total, st>>>(p);
   RVQ_LAUNCH_CHECK("tc_encode_kernel");
   if (a.quantized != nullptr)
     return simt_quant_sum(a.pack, a.K, a.D, a.x, p.fa, N, a.T, a.stage0, a.n_q, a.codes, a.quantized, p.ste,
