@@ -124,9 +124,9 @@ __device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
 }
 
 // tiles [start, start+cnt) of this CTA
-__device__ __forceinline__ void cta_range(int64_t ntiles, int64_t& start, int64_t& cnt) {
-  const int64_t base = ntiles / gridDim.x, rem = ntiles % gridDim.x;
-  const int64_t b = blockIdx.x;
+__device__ __forceinline__ void cta_range(int ntiles, int& start, int& cnt) {
+  const int base = ntiles / int(gridDim.x), rem = ntiles % int(gridDim.x);
+  const int b = blockIdx.x;
   start = b * base + (b < rem ? b : rem);
   cnt = base + (b < rem ? 1 : 0);
 }
@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   // every CTA walks the chunks of a stage in its own rotation, so that the 148 SMs (which run the same stage
   // at about the same time) do not all pull the same lines out of the same L2 slices at once
   const int rot = int(blockIdx.x % unsigned(nchunks));
-  const int64_t ntiles = (p.N + kM - 1) / kM;
-  int64_t tile0, tcnt;
+  const int ntiles = int((p.N + kM - 1) / kM);       // N < 2^31 frames per call (checked by rvq_encode)
+  int tile0, tcnt;
   cta_range(ntiles, tile0, tcnt);
 
   if (threadIdx.x == 0) {
@@ -472,12 +472,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
 
   // register budget: the two frame warpgroups take what the producer / issuer warpgroup gives up
   if (warp >= 8) {
-  ptx::reg_dec<72>();
+  ptx::reg_dec<64>();
   if (warp == 8) {
     // ===== TMA producer: the chunk stream (stage-major) of every tile =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t t = 0; t < tcnt; ++t) {
+      for (int t = 0; t < tcnt; ++t) {
         for (int s = 0; s < p.n_q; ++s) {
           const unsigned char* img = pv.tc(p.stage0 + s);
 #ifdef RVQ_TC_TMA_AFTER_A
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     __syncwarp();
   }
   } else {
-    ptx::reg_inc<208>();
+    ptx::reg_inc<216>();
     // ===== frame warps =====
     const int q = warp & 3;                    // TMEM lane quadrant = frames 32q..32q+31 of the tile
     const int h = warp >= 4 ? 1 : 0;           // 0 = score warp, 1 = helper warp
@@ -550,8 +550,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     const long long t_begin = clock64();
 #endif
     uint32_t acc_it = 0;
-    for (int64_t t = 0; t < tcnt; ++t) {
-      const int64_t tile_n0 = (tile0 + t) * kM;
+    for (int t = 0; t < tcnt; ++t) {
+      const int64_t tile_n0 = int64_t(tile0 + t) * kM;
       const int t_tile = int(t);
 #ifdef RVQ_TC_TIMERS
       unsigned tc0 = (unsigned)clock();
