@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 
 namespace rvq {
 
@@ -89,7 +90,9 @@ int rvq_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int6
   cudaStream_t st = (cudaStream_t)stream;
   EncodeArgs a{pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, residual_out, stage_sqerr, flags};
   const bool want_tc = tc_shape(K, D) && !(flags & (RVQ_FLAG_FORCE_EXACT | RVQ_FLAG_DIRECT_DIST));
-  return want_tc ? tc_encode(a, st) : simt_encode(a, st);
+  if (!want_tc) return simt_encode(a, st);
+  static const int impl = [] { const char* e = getenv("RVQ_TC_IMPL"); return e ? atoi(e) : 2; }();
+  return impl == 1 ? tc_encode(a, st) : tc2_encode(a, st);
 }
 
 int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int64_t N, int64_t* buckets, void* stream) {
