@@ -45,9 +45,27 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// blocking wait: try_wait with a suspend-time hint parks the warp in hardware until the phase completes (or the hint
+// expires), instead of spinning through the issue slots and the instruction cache of the working warps
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef RVQ_MBAR_SPIN
   while (!mbar_try_wait(bar, parity)) {
   }
+#else
+  while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+  }
+#endif
 }
 
 // ---- bulk async copy global -> shared (TMA engine, 1-D), completion on an mbarrier ---------------

@@ -15,12 +15,14 @@
 //                TMA engine (cp.async.bulk) from the L2-resident pack into a ring of 7 third-of-a-chunk
 //                slots (6 K-groups = 12 KB each; small slots keep more bytes in flight than whole chunks would);
 //            D = 3 accumulator buffers of 128 TMEM columns shared by both slots.
-//   warps    0..3  score warps  (thread = TMEM lane = frame): tcgen05.ld, per-class / per-batch minima, certified
-//                  winner or candidate list (see below), codes of certified frames;
-//            4..7  update warps: gather of the winners' fp32 rows ("lane = dimension", a quarter-warp per frame, eight
-//                  rows in flight per quarter-warp), exact fp32 re-score of candidate lists, r <- r - q, then the
-//                  fp16 operand of the next stage goes to tensor memory (thread = frame, tcgen05.st); tile loads;
-//            8, 10, 11  TMA producers (one K-third of every chunk each);  9  MMA issuer (owns the TMEM allocation).
+//   warps    0..3   score warps  (thread = TMEM lane = frame): tcgen05.ld, per-class / per-batch minima, certified
+//                   winner or candidate list (see below), codes of certified frames;
+//            4..11  update warps: gather of the winners' fp32 rows ("lane = dimension", a quarter-warp per frame, four
+//                   rows in flight per quarter-warp), exact fp32 re-score of candidate lists, r <- r - q; then, thread =
+//                   frame, the fp16 operand of the next stage goes to tensor memory (tcgen05.st) together with its
+//                   exact rounding residue; tile loads;
+//            12  TMA producer;  13  MMA issuer (owns the TMEM allocation).
+//            setmaxnreg: 160 registers for the score warps, 152 for the update warps, 48 for the last warpgroup.
 //   sync     mbarriers only between roles: a_ready[slot] (update -> MMA), acc_full/acc_empty (MMA <-> score),
 //            cand_ready[slot] (score -> update), full/empty (TMA <-> MMA).
 //
@@ -43,7 +45,12 @@ constexpr int kRing = 7;                // B ring slots; each holds one K-third 
 constexpr int kSlotBytes = 6 * kTcLBO;  // 12288 B
 constexpr int kAccBufs = 3;             // accumulator buffers of kN TMEM columns
 constexpr int kTmemA = kAccBufs * kN;   // first TMEM column of the fp16 operands (64 columns per slot)
-constexpr int kThreadsTc = 12 * 32;
+constexpr int kThreadsTc = 16 * 32;
+constexpr int kUpdWarps = 8;
+#ifndef RVQ_TC_WIN
+#define RVQ_TC_WIN 3
+#endif
+constexpr int kWin = RVQ_TC_WIN;          // winner rows in flight per quarter-warp
 constexpr int kBig = 5;                 // ncnt marker: more than 4 candidates (enumerate the masks)
 constexpr int kFull = 6;                // ncnt marker: exact scan of the whole table
 constexpr int kRsBytes = kM * 128 * 4;  // fp32 residual of one tile
@@ -55,11 +62,10 @@ struct Sm {
   static constexpr uint32_t misc = rs + 2 * kRsBytes;              // 2 x per-slot block (offsets m_*)
   static constexpr uint32_t m_cand = 0;                            // int4 [128]: candidate codes (-1 = none)
   static constexpr uint32_t m_ncnt = m_cand + kM * 16;             // int [128]
-  static constexpr uint32_t m_cmask = m_ncnt + kM * 4;             // u32 [128] flagged classes
-  static constexpr uint32_t m_bmask = m_cmask + kM * 4;            // u32 [128] flagged batches
-  static constexpr uint32_t m_dr2 = m_bmask + kM * 4;              // float [128]: |r - fp16(r)|^2 of the current operand
-  static constexpr uint32_t m_xx = m_dr2 + kM * 4;                 // float [128]: |x|^2 of a freshly loaded tile
-  static constexpr uint32_t m_slowq = m_xx + kM * 4;               // u8 [128]: frames with 2..4 listed candidates
+  static constexpr uint32_t m_cmask = m_ncnt + kM * 4;             // u32 [128] flagged classes   (a fresh tile: |x|^2 of dims 0..63)
+  static constexpr uint32_t m_bmask = m_cmask + kM * 4;            // u32 [128] flagged batches   (a fresh tile: |x|^2 of dims 64..127)
+  static constexpr uint32_t m_dr2 = m_bmask + kM * 4;              // float [2][128]: |r - fp16(r)|^2 of the current operand, per half of the dims
+  static constexpr uint32_t m_slowq = m_dr2 + 2 * kM * 4;          // u8 [128]: frames with 2..4 listed candidates
   static constexpr uint32_t m_wideq = m_slowq + kM;                // u8 [128]: frames with a wide candidate set
   static constexpr uint32_t m_qcnt = m_wideq + kM;                 // int [2]: queue lengths {slow, wide}
   static constexpr uint32_t m_size = m_qcnt + 16;
@@ -207,72 +213,58 @@ __device__ __forceinline__ float dot_row(const Row4& a, const Row4& b) {
 // exact fp32 r <- r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training), the exact squared
 // rounding residue |r - fp16(r)|^2 of the new residual (it enters the score-error margin of the next stage) and
 // the squared-error partial.  Called by whole quarter-warps (8 converged lanes; all lanes of the warp shuffle).
-// squared rounding residue of a float4 against its fp16 image
-__device__ __forceinline__ float residue4(const float4& v) {
-  uint32_t w0, w1;
-  return residue2(v.z, v.w, w1, residue2(v.x, v.y, w0, 0.f));
-}
 // new residual n = r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training)
 template <bool TRAIN>
 __device__ __forceinline__ float4 sub_row(const TcParams& p, const float4& rv, float4 q) {
   if (TRAIN && p.ste) { q.x = rv.x + (q.x - rv.x); q.y = rv.y + (q.y - rv.y); q.z = rv.z + (q.z - rv.z); q.w = rv.w + (q.w - rv.w); }
   return make_float4(rv.x - q.x, rv.y - q.y, rv.z - q.z, rv.w - q.w);
 }
-// exact fp32 r <- r - q for a frame at an arbitrary position (queue / wide paths), the exact squared rounding
-// residue |r - fp16(r)|^2 of the new residual (it enters the score-error margin of the next stage; this lane's
-// share) and the squared-error partial.
+// exact fp32 r <- r - q for a frame at an arbitrary position (candidate-list / wide paths)
 template <bool TRAIN>
-__device__ __forceinline__ void apply_row(const TcParams& p, float* rs, int f, int j, const Row4& r,
-                                          const Row4& qrow, bool valid_frame, float& sq_acc, float& e2_out) {
-  Row4 n;
-  float e[4];
+__device__ __forceinline__ void apply_row(const TcParams& p, float* rs, int f, int j, const Row4& r, const Row4& qrow) {
   #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    n.v[i] = sub_row<TRAIN>(p, r.v[i], qrow.v[i]);
-    *reinterpret_cast<float4*>(rs + rs_off(f, 8 * i + j)) = n.v[i];
-    e[i] = residue4(n.v[i]);
-  }
-  if (TRAIN && p.sqerr != nullptr && valid_frame) sq_acc += dot_row(n, n);
-  e2_out = (e[0] + e[1]) + (e[2] + e[3]);
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(rs + rs_off(f, 8 * i + j)) = sub_row<TRAIN>(p, r.v[i], qrow.v[i]);
 }
 
 // A frame whose flagged batches x flagged classes give more than 4 candidates: the whole warp works on it,
-// 16 candidates per step (4 per quarter-warp); the quarter that holds the winner's row updates the frame.
-struct Cand4 { int c[4]; Row4 w[4]; float nrm[4]; };
-__device__ __forceinline__ void load4(Cand4& k, int j, const float* __restrict__ t32, const float* __restrict__ cn) {
+// 8 candidates per step (2 per quarter-warp); the quarter that found the winner updates the frame.
+template <int NC> struct Cand { int c[NC]; Row4 w[NC]; float nrm[NC]; };
+template <int NC>
+__device__ __forceinline__ void load_cand(Cand<NC>& k, int j, const float* __restrict__ t32, const float* __restrict__ cn) {
   #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < NC; ++u) {
     k.nrm[u] = 0.f;
     if (k.c[u] >= 0) { k.w[u] = load_row(t32, k.c[u], j); k.nrm[u] = __ldg(cn + k.c[u]); }
   }
 }
-__device__ __forceinline__ void score4(const Cand4& k, const Row4& r, float rr, float& best, int& bcode, Row4& brow) {
-  float d[4];
+// exact distances of up to NC candidates (core_vq.py:183-187); keeps the best (lowest code on ties) and its slot u
+template <int NC>
+__device__ __forceinline__ void score_cand(const Cand<NC>& k, const Row4& r, float rr, float& best, int& bcode, int& bidx) {
+  float d[NC];
   #pragma unroll
-  for (int u = 0; u < 4; ++u) d[u] = dot_row(r, k.w[u]);
+  for (int u = 0; u < NC; ++u) d[u] = dot_row(r, k.w[u]);
   #pragma unroll
   for (int off = 4; off > 0; off >>= 1) {
     #pragma unroll
-    for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], off);
+    for (int u = 0; u < NC; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], off);
   }
   #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < NC; ++u) {
     const float e = (rr - 2.f * d[u]) + k.nrm[u];
-    if (k.c[u] >= 0 && (e < best || (e == best && k.c[u] < bcode))) { best = e; bcode = k.c[u]; brow = k.w[u]; }
+    if (k.c[u] >= 0 && (e < best || (e == best && k.c[u] < bcode))) { best = e; bcode = k.c[u]; bidx = u; }
   }
 }
 template <bool TRAIN>
-__device__ __forceinline__ float resolve_wide(const TcParams& p, float* rs, unsigned char* ms, int f, int lane, int s, int rot, int nchunks,
-                                           int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn) {
-  float sq_acc = 0.f;
+__device__ __forceinline__ void resolve_wide(const TcParams& p, float* rs, unsigned char* ms, int f, int lane, int s, int rot, int nchunks,
+                                             int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn) {
   const int qq = lane >> 3, j = lane & 7;
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
   const uint32_t bm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + f * 4);
   const int nc = __popc(cm);
   const Row4 r = load_res(rs, f, j);
   const float rr = quarter_sum(dot_row(r, r));
-  float best = inf_f(); int bcode = 0x7fffffff; Row4 brow = r;
-  // quarter qq takes the flagged batches number qq, qq + 4, ...; within a batch the flagged classes four at a time
+  float best = inf_f(); int bcode = 0x7fffffff, bidx = 0;
+  // quarter qq takes the flagged batches number qq, qq + 4, ...; within a batch the flagged classes two at a time
   uint32_t bmq = bm;
   for (int i = 0; i < qq; ++i) bmq &= bmq - 1;
   const int nb = __popc(bm);
@@ -285,16 +277,16 @@ __device__ __forceinline__ float resolve_wide(const TcParams& p, float* rs, unsi
     if (a >= 0) { int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks; base = pc * 128 + (a & 3) * 32; }   // processing order -> code
     uint32_t cmq = cm;
     #pragma unroll 1
-    for (int oc = 0; oc < nc; oc += 4) {
-      Cand4 k;
+    for (int oc = 0; oc < nc; oc += 2) {
+      Cand<2> k;
       #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int jj = cmq ? __ffs(cmq) - 1 : -1;
         cmq &= cmq - 1;
         k.c[u] = (a >= 0 && jj >= 0) ? base + jj : -1;
       }
-      load4(k, j, t32, cn);
-      score4(k, r, rr, best, bcode, brow);
+      load_cand<2>(k, j, t32, cn);
+      score_cand<2>(k, r, rr, best, bcode, bidx);
     }
   }
   // best over the four quarters (candidate codes are distinct, so the winner's quarter is unique)
@@ -309,126 +301,138 @@ __device__ __forceinline__ float resolve_wide(const TcParams& p, float* rs, unsi
   if (wc == 0x7fffffff) {                                  // NaN distances only: lowest candidate, like an exact scan would
     mine = qq == 0;
     if (mine) { const int c0 = (__ffs(bm) - 1); int pc = (c0 >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
-                bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); brow = load_row(t32, bcode, j); }
+                bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); }
   }
-  // every lane runs the arithmetic (shuffles inside), only the winner's quarter stores
-  float e2 = 0.f;
   const int64_t nfr = tile_n0 + f;
   if (mine) {
-    apply_row<TRAIN>(p, rs, f, j, r, brow, nfr < p.N, sq_acc, e2);
+    apply_row<TRAIN>(p, rs, f, j, r, load_row(t32, bcode, j));     // the winner's row again (rare path; an L1/L2 hit)
     if (j == 0 && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
   }
-  e2 = quarter_sum(e2);
-  if (mine && j == 0) reinterpret_cast<float*>(ms + Sm::m_dr2)[f] = e2;
-  return sq_acc;
 }
 
-// The update of one (slot, stage): executed by the four update warps.
-//   1. certified frames: quarter-warp qq of warp q owns frames 32q + 8qq .. +7; the eight winner rows are put in flight
-//      at once (two register buffers of four rows), then applied one after the other;
-//   2. frames with a candidate list (2..4 codes) come from the slot's queue, spread over the 16 quarter-warps:
-//      the four candidate rows are loaded together and re-scored in exact fp32 (core_vq.py:183-187);
-//   3. frames with wide candidate sets: one frame per warp at a time (resolve_wide).
+// The residual update of one (slot, stage), executed by the eight update warps (u = 0..7: TMEM lane quadrant q = u & 3,
+// half h = u >> 2 of its 32 frames).
+//   1. frames with wide candidate sets: one frame per warp at a time (resolve_wide);
+//   2. certified frames, branch-free: quarter-warp qq owns frames f0 .. f0+3 (f0 = 32q + 16h + 4qq).  Lane j works on the
+//      16-byte slots 8(i ^ ix) + j (i = 0..3) of each residual row; with the row swizzle of rs_off that slot holds the
+//      logical chunk 8i + (j ^ jx) of the frame, so the winner's row is fetched with its 16-byte pieces permuted by
+//      jx (the 8 lanes of a quarter still cover one contiguous 128-byte segment per i; all addresses are a base +
+//      an immediate).  All
+//      four rows are in flight at once.  A queued frame's slot fetches row 0 and its stores are predicated off;
+//   3. frames with a candidate list (2..4 codes) come from the slot's queue, spread over the 32 quarter-warps:
+//      the four candidate rows are loaded together and re-scored in exact fp32 (core_vq.py:183-187).
 template <bool TRAIN>
-__device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsigned char* ms, int q, int lane, int s, int rot,
+__device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsigned char* ms, int u, int lane, int s, int rot,
                                             int nchunks, int64_t tile_n0, const float* __restrict__ t32,
-                                            const float* __restrict__ cn, float& sq_acc, uint32_t (&tsub)[4]) {
+                                            const float* __restrict__ cn, uint32_t (&tsub)[4]) {
   const int qq = lane >> 3, j = lane & 7;
-  const int fbase = q * 32;
+  const int q = u & 3, h = u >> 2;
+  const int fbase = q * 32 + h * 16;
   RVQ_TICK0();
   const int* qc = reinterpret_cast<const int*>(ms + Sm::m_qcnt);
   const int nslow = qc[0], nwide = qc[1];
   const unsigned char* slowq = ms + Sm::m_slowq;
   const unsigned char* wideq = ms + Sm::m_wideq;
-  float* dr2 = reinterpret_cast<float*>(ms + Sm::m_dr2);
-  const int nv = *reinterpret_cast<const int*>(ms + Sm::m_ncnt + (fbase + lane) * 4);
+  const int nv = lane < 16 ? *reinterpret_cast<const int*>(ms + Sm::m_ncnt + (fbase + lane) * 4) : 1;
   const uint32_t slow = __ballot_sync(0xffffffffu, nv > 1);     // bit i = frame fbase+i is in one of the queues
   const int4* cand = reinterpret_cast<const int4*>(ms + Sm::m_cand);
-  const int gq = q * 4 + qq;                                    // quarter-warp number among the update warps, 0..15
-
-  // wide candidate sets (a function call: nothing may be in flight across it): one frame per warp at a time
-  #pragma unroll 1
-  for (int i = q; i < nwide; i += 4) sq_acc += resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
-  RVQ_TICK(tsub[0]);
-  // ---- certified frames, branch-free: quarter-warp qq owns frames f0 .. f0+7 (f0 = 32q + 8qq).  Lane j works on the
-  // physical 16-byte slots 8i + j (i = 0..3) of each residual row (addresses = one base + immediates); with the row
-  // swizzle of rs_off that slot holds the logical chunk 8(i ^ qq) + (j ^ k) of frame f0 + k, so the winner's row is
-  // fetched in that permutation (the 8 lanes of a quarter still cover one contiguous 128-byte segment per i).
-  // All eight rows are in flight at once.  A queued frame's slot fetches row 0 and its stores are predicated off.
-  const int f0 = fbase + 8 * qq;
-  float* rbase = rs + f0 * 128 + 4 * j;
-  int oc[8];
-  #pragma unroll
-  for (int k = 0; k < 8; ++k) oc[k] = ((slow >> (8 * qq + k)) & 1u) ? -1 : cand[f0 + k].x;
-  Row4 buf[8];
-  #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float* rp = t32 + size_t(oc[k] >= 0 ? oc[k] : 0) * 128 + 4 * (j ^ k);
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) buf[k].v[i] = __ldg(reinterpret_cast<const float4*>(rp + 32 * (i ^ qq)));
-  }
-  float e[8];
-  #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const bool ok = oc[k] >= 0;
-    Row4 n;
-    float ei[4];
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4* rp = reinterpret_cast<float4*>(rbase + k * 128 + 32 * i);
-      n.v[i] = sub_row<TRAIN>(p, *rp, buf[k].v[i]);
-      if (ok) *rp = n.v[i];
-      ei[i] = residue4(n.v[i]);
-    }
-    e[k] = (ei[0] + ei[1]) + (ei[2] + ei[3]);
-    if (TRAIN && p.sqerr != nullptr && ok && tile_n0 + f0 + k < p.N) sq_acc += dot_row(n, n);
-  }
-  // reduce-scatter over the quarter: lane j ends with the residue of frame f0 + j (7 shuffles instead of 24)
   {
-    float a4[4], a2[2];
+    const int f0 = fbase + 4 * qq;
+    const int ix = 2 * h + (qq >> 1), jx0 = 4 * (qq & 1);
+    // physical slot 8(i ^ ix) + j of frame f0 + k holds the logical chunk 8i + (j ^ (jx0 + k)): four shared-memory bases
+    // (one per i) + immediates on the residual side, one row pointer per frame + immediates on the table side
+    float* rb[4];
     #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const float keep = (j & 4) ? e[m + 4] : e[m], give = (j & 4) ? e[m] : e[m + 4];
-      a4[m] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
-    }
+    for (int i = 0; i < 4; ++i) rb[i] = rs + f0 * 128 + 32 * (i ^ ix) + 4 * j;
+    int oc[4];
     #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const float keep = (j & 2) ? a4[m + 2] : a4[m], give = (j & 2) ? a4[m] : a4[m + 2];
-      a2[m] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+    for (int k = 0; k < 4; ++k) oc[k] = ((slow >> (4 * qq + k)) & 1u) ? -1 : cand[f0 + k].x;
+    // a rolling window of kWin rows in flight: the buffer of frame k is refilled with the row of frame k + kWin
+    Row4 buf[kWin];
+    auto fetch = [&](int k) {
+#ifdef RVQ_EXP_ROW0       // experiment (wrong results): every gather hits the same L1-resident row
+      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(oc[k] >= 0 ? 0 : 0) * 128 + 4 * (j ^ (jx0 + k)));
+#else
+      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(oc[k] >= 0 ? oc[k] : 0) * 128 + 4 * (j ^ (jx0 + k)));
+#endif
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) buf[k % kWin].v[i] = __ldg(rp + 8 * i);
+    };
+    #pragma unroll
+    for (int k = 0; k < kWin; ++k) fetch(k);
+    RVQ_TICK(tsub[0]);
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 r[4];
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = *reinterpret_cast<const float4*>(rb[i] + k * 128);
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 n = sub_row<TRAIN>(p, r[i], buf[k % kWin].v[i]);
+        if (oc[k] >= 0) *reinterpret_cast<float4*>(rb[i] + k * 128) = n;
+      }
+      if (k + kWin < 4) fetch(k + kWin);
     }
-    const float keep = (j & 1) ? a2[1] : a2[0], give = (j & 1) ? a2[0] : a2[1];
-    const float tot = keep + __shfl_xor_sync(0xffffffffu, give, 1);
-    if (!((slow >> (8 * qq + j)) & 1u)) dr2[f0 + j] = tot;
   }
   RVQ_TICK(tsub[1]);
-  // candidate lists: items gq, gq + 16, ...
+  // candidate lists: item qi goes to quarter qi / 8 of warp qi % 8 (the first eight items land on eight different
+  // warps), then qi + 32, ...; a warp none of whose quarters has an item skips the body
+  const int gq = qq * kUpdWarps + u;
   #pragma unroll 1
-  for (int qi = gq; qi < ((nslow + 15) & ~15); qi += 16) {
+  for (int qi = gq; qi < ((nslow + 31) & ~31); qi += 32) {
     const int f = qi < nslow ? int(slowq[qi]) : -1;
+    if (!__any_sync(0xffffffffu, f >= 0)) continue;
     int4 cd = make_int4(-1, -1, -1, -1);
     if (f >= 0) cd = cand[f];
-    Cand4 k;
+    Cand<4> k;
     k.c[0] = cd.x; k.c[1] = cd.y; k.c[2] = cd.z; k.c[3] = cd.w;
-    load4(k, j, t32, cn);
+    load_cand<4>(k, j, t32, cn);
     Row4 r;
     #pragma unroll
     for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f >= 0) r = load_res(rs, f, j);
     const float rr = quarter_sum(dot_row(r, r));
     // core_vq.py:183-187, lowest index on ties; NaN distances: keep the first candidate unless a finite one exists
-    float best = inf_f(); int bcode = 0x7fffffff; Row4 brow = k.w[0];
-    score4(k, r, rr, best, bcode, brow);
+    float best = inf_f(); int bcode = 0x7fffffff, bidx = 0;
+    score_cand<4>(k, r, rr, best, bcode, bidx);
     if (bcode == 0x7fffffff) bcode = cd.x;
-    float e2 = 0.f;
     const int64_t nfr = tile_n0 + f;
     if (f >= 0) {
-      apply_row<TRAIN>(p, rs, f, j, r, brow, nfr < p.N, sq_acc, e2);
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a01 = bidx == 1 ? k.w[1].v[i] : k.w[0].v[i], a23 = bidx == 3 ? k.w[3].v[i] : k.w[2].v[i];
+        *reinterpret_cast<float4*>(rs + rs_off(f, 8 * i + j)) = sub_row<TRAIN>(p, r.v[i], bidx >= 2 ? a23 : a01);
+      }
       if (j == 0 && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
     }
-    e2 = quarter_sum(e2);
-    if (f >= 0 && j == 0) dr2[f] = e2;
   }
   RVQ_TICK(tsub[2]);
+  // frames with wide candidate sets: one frame per warp at a time, handed out from the last warp down (the candidate
+  // lists start at the first)
+  #pragma unroll 1
+  for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
+  RVQ_TICK(tsub[3]);
+}
+
+// Thread = frame = TMEM lane (f = 32q + lane), dims 64h .. 64h+63 of the new residual: fp16 operand of the next stage
+// to tensor memory (16 dims per tcgen05.st), its exact squared rounding residue |r - fp16(r)|^2 (it enters the score
+// margin of the next stage) and, in training, the squared-error partial sum((q - r)^2) = |new residual|^2 (core_vq.py:319).
+template <bool TRAIN>
+__device__ __forceinline__ void operand_pass(const float* rs, unsigned char* ms, int f, int h, uint32_t taddr, bool store, float& sq) {
+  float e[4] = {0.f, 0.f, 0.f, 0.f};
+  #pragma unroll 2
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[8];
+    #pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 * h + 4 * g + c));
+      e[c] = residue2(v.x, v.y, w[2 * c], e[c]);
+      e[c] = residue2(v.z, v.w, w[2 * c + 1], e[c]);
+      if (TRAIN) sq = dot4(v, v, sq);
+    }
+    if (store) ptx::tmem_st8(taddr + 32 * h + 8 * g, w);
+  }
+  reinterpret_cast<float*>(ms + Sm::m_dr2)[h * kM + f] = (e[0] + e[1]) + (e[2] + e[3]);
 }
 
 }  // namespace
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1); }
     for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->a_ready[i]), 4); ptx::mbar_init(ptx::smem_u32(&bars->cand_ready[i]), 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->a_ready[i]), kUpdWarps); ptx::mbar_init(ptx::smem_u32(&bars->cand_ready[i]), 4); }
     ptx::fence_mbar_init();
   }
   if (threadIdx.x < 2) {
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
   // constant augmented K block of A: k-group 0 = (1, 1, 0, ...) picks up hi/lo of |c|^2, k-group 1 = 0
   for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
     *reinterpret_cast<uint4*>(smem + Sm::aug + i * 16) = make_uint4(i < 128 ? pack_half2(1.f, 1.f) : 0u, 0u, 0u, 0u);
-  if (warp == 9) {
+  if (warp == 13) {
     ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
     ptx::tmem_relinquish();
   }
@@ -474,31 +478,33 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp >= 8) {
-    ptx::reg_dec<40>();
-    if (warp != 9) {
-      // ===== TMA producers: warp 8 / 10 / 11 copies K-third 0 / 1 / 2 of every 128-code chunk, in the global step order =====
+  if (warp >= 12) {
+    ptx::reg_dec<48>();
+    if (warp == 12) {
+      // ===== TMA producer: the three K-thirds of every 128-code chunk, in the global step order.  One thread: the slots
+      // come free in the order they were filled, and a spinning warp costs the working warps of its scheduler issue slots =====
       if (lane == 0) {
-        const uint32_t third = warp == 8 ? 0u : uint32_t(warp - 9);
-        uint32_t it = 0;                       // chunk counter
+        uint32_t slot = 0, ph = 0;             // ring position of the next K-third
         for (int n = 0; n < steps0; ++n) {
           for (int X = 0; X < 2; ++X) {
             if (X == 1 && n >= steps1) break;
-            const unsigned char* img = pv.tc(p.stage0 + n % p.n_q) + third * kSlotBytes;
-            for (int c = 0; c < nchunks; ++c, ++it) {
+            const unsigned char* img = pv.tc(p.stage0 + n % p.n_q);
+            for (int c = 0; c < nchunks; ++c) {
               const int pc = c + rot < nchunks ? c + rot : c + rot - nchunks;
-              const uint32_t t3 = 3 * it + third;
-              const uint32_t slot = t3 % kRing, ph = (t3 / kRing) & 1;
-              ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), ph ^ 1);
-              const uint32_t fb = ptx::smem_u32(&bars->full[slot]);
-              ptx::mbar_expect_tx(fb, kSlotBytes);
-              ptx::bulk_g2s(sbase + Sm::ring + slot * kSlotBytes, img + size_t(pc) * kTcChunkBytes, kSlotBytes, fb);
+              #pragma unroll 1
+              for (int third = 0; third < 3; ++third) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), ph ^ 1);
+                const uint32_t fb = ptx::smem_u32(&bars->full[slot]);
+                ptx::mbar_expect_tx(fb, kSlotBytes);
+                ptx::bulk_g2s(sbase + Sm::ring + slot * kSlotBytes, img + size_t(pc) * kTcChunkBytes + third * kSlotBytes, kSlotBytes, fb);
+                if (++slot == kRing) { slot = 0; ph ^= 1; }
+              }
             }
           }
         }
       }
       __syncwarp();
-    } else {
+    } else if (warp == 13) {
       // ===== MMA issuer: per chunk 8 MMAs with A from tensor memory + 1 with the constant shared-memory block =====
       if (lane == 0) {
         constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
@@ -507,7 +513,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
 #ifdef RVQ_TC_TIMERS
         uint32_t m_wa = 0, m_wf = 0, m_wc = 0, m_is = 0; const long long m_t0 = clock64();
 #endif
-        uint32_t it = 0;
+        uint32_t slot = 0, ph = 0, buf = 0, bph = 0;      // ring slot / phase of the next K-third, accumulator buffer / phase
         for (int n = 0; n < steps0; ++n) {
           for (int X = 0; X < 2; ++X) {
             if (X == 1 && n >= steps1) break;
@@ -516,15 +522,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
             ptx::tc_fence_after();
             RVQ_TICK(m_wa);
             const uint32_t a_tmem = tmem + kTmemA + 64 * X;
-            for (int c = 0; c < nchunks; ++c, ++it) {
-              const uint32_t buf = it % kAccBufs;
-              ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), ((it / kAccBufs) & 1) ^ 1);   // accumulator drained
+            for (int c = 0; c < nchunks; ++c) {
+              ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), bph ^ 1);                     // accumulator drained
               RVQ_TICK(m_wc);
               const uint32_t d_tmem = tmem + buf * kN;
               #pragma unroll
               for (int h = 0; h < 3; ++h) {
-                const uint32_t t3 = 3 * it + h, slot = t3 % kRing;
-                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), (t3 / kRing) & 1);              // K-third landed
+                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), ph);                            // K-third landed
                 ptx::tc_fence_after();
                 RVQ_TICK(m_wf);
                 const uint64_t bs = bd0 + uint64_t((slot * kSlotBytes) >> 4);
@@ -535,9 +539,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
                   else ptx::umma_f16_ts(d_tmem, a_tmem + 8 * (3 * h + k), bk, idesc, (h | k) ? 1u : 0u);
                 }
                 ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));   // ring slot reusable once read
+                if (++slot == kRing) { slot = 0; ph ^= 1; }
                 RVQ_TICK(m_is);
               }
               ptx::umma_commit(ptx::smem_u32(&bars->acc_full[buf]));   // scores ready for the score warps
+              if (++buf == kAccBufs) { buf = 0; bph ^= 1; }
             }
           }
         }
@@ -552,16 +558,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
       __syncwarp();
     }
   } else if (warp >= 4) {
-    ptx::reg_inc<232>();
+    ptx::reg_inc<152>();
     // ===== update warps =====
-    const int q = warp - 4;                    // TMEM lane quadrant = frames 32q..32q+31 of a tile
+    const int u = warp - 4;
+    const int q = u & 3, h = u >> 2;           // TMEM lane quadrant (frames 32q..32q+31 of a tile), half of the dims / of the frames
     const int f = q * 32 + lane;               // thread <-> frame mapping of tile loads and operand stores
     const uint32_t tq = tmem + (uint32_t(q * 32) << 16) + kTmemA;
 #ifdef RVQ_TC_TIMERS
-    uint32_t t_wait = 0, t_upd = 0, t_tr = 0, t_load = 0, t_stw = 0;
+    uint32_t t_wait = 0, t_upd = 0, t_tr = 0, t_load = 0, t_stw = 0, t_bar = 0;
 #endif
     uint32_t tsub[4] = {0u, 0u, 0u, 0u};     // (timers) wide sets / own frames / candidate lists / barrier
-    // load the latent tile `tile` into slot X: fp32 residual rows, |x|^2, fp16 operand in tensor memory, rounding residue
+    // load dims 64h..64h+63 of the latent tile `tile` into slot X: fp32 residual rows, |x|^2, fp16 operand in tensor
+    // memory, rounding residue
     auto load_tile = [&](int X, int tile) {
       float* rs = reinterpret_cast<float*>(smem + Sm::rs + X * kRsBytes);
       unsigned char* ms = smem + Sm::misc + X * Sm::m_size;
@@ -569,30 +577,32 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
       const bool valid = n < p.N;
       const int64_t xb = valid ? p.fa.base(n) : 0;
       float xsum = 0.f, e2 = 0.f;
-      #pragma unroll 1
-      for (int hb = 0; hb < 4; ++hb) {
-        float v[32];
-        const int d0 = hb * 32;
-        #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = valid ? __ldg(p.x + xb + int64_t(d0 + j) * p.fa.sxd) : 0.f;
-        float pt = 0.f;
-        #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          *reinterpret_cast<float4*>(rs + rs_off(f, (d0 + j) >> 2)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          pt = fmaf(v[j], v[j], pt); pt = fmaf(v[j + 1], v[j + 1], pt);
-          pt = fmaf(v[j + 2], v[j + 2], pt); pt = fmaf(v[j + 3], v[j + 3], pt);
-        }
-        xsum = hb == 0 ? pt : xsum + pt;                    // ((p0 + p1) + p2) + p3, the exact path's order
-        uint32_t w0[8], w1[8];
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) e2 = residue2(v[2 * j], v[2 * j + 1], w0[j], e2);
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) e2 = residue2(v[16 + 2 * j], v[16 + 2 * j + 1], w1[j], e2);
-        ptx::tmem_st8(tq + 64 * X + hb * 16, w0);
-        ptx::tmem_st8(tq + 64 * X + hb * 16 + 8, w1);
+      // the warp's 64 lines (one per dim: 32 consecutive frames x 4 B) are asked for at once, then read 16 dims at a time
+      if (valid) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + lane) * p.fa.sxd));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + 32 + lane) * p.fa.sxd));
       }
-      reinterpret_cast<float*>(ms + Sm::m_xx)[f] = xsum;
-      reinterpret_cast<float*>(ms + Sm::m_dr2)[f] = e2;
+      #pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        float v[16];
+        const int d0 = h * 64 + g * 16;
+        const float* xp = p.x + xb + int64_t(d0) * p.fa.sxd;
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = valid ? __ldg(xp + int64_t(j) * p.fa.sxd) : 0.f;
+        uint32_t w[8];
+        #pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(rs + rs_off(f, (d0 + j) >> 2)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          xsum = fmaf(v[j], v[j], xsum); xsum = fmaf(v[j + 1], v[j + 1], xsum);
+          xsum = fmaf(v[j + 2], v[j + 2], xsum); xsum = fmaf(v[j + 3], v[j + 3], xsum);
+          e2 = residue2(v[j], v[j + 1], w[j / 2], e2);
+          e2 = residue2(v[j + 2], v[j + 3], w[j / 2 + 1], e2);
+        }
+        ptx::tmem_st8(tq + 64 * X + d0 / 2, w);
+      }
+      // |x|^2 of this half of the dims goes where the (not yet written) class / batch masks of the tile's first stage live
+      reinterpret_cast<float*>(ms + (h ? Sm::m_bmask : Sm::m_cmask))[f] = xsum;
+      reinterpret_cast<float*>(ms + Sm::m_dr2)[h * kM + f] = e2;
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -611,28 +621,21 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
           const int64_t tile_n0 = int64_t(tile0 + X + 2 * jt) * kM;
           float* rs = reinterpret_cast<float*>(smem + Sm::rs + X * kRsBytes);
           unsigned char* ms = smem + Sm::misc + X * Sm::m_size;
-          ptx::mbar_wait(ptx::smem_u32(&bars->cand_ready[X]), uint32_t(n) & 1);      // winners / candidate lists of this step
+          // winners / candidate lists of this step: one warp polls the mbarrier, the others block on a hardware barrier
+          // (a blocked warp costs no issue slots, a polling one does)
+          if (u == 0) ptx::mbar_wait(ptx::smem_u32(&bars->cand_ready[X]), uint32_t(n) & 1);
+          ptx::named_bar_sync(8, kUpdWarps * 32);
           RVQ_TICK(t_wait);
-          float sq = 0.f;
-          update_pass<TRAIN>(p, rs, ms, q, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st), sq, tsub);
+          update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st), tsub);
           RVQ_TICK(t_upd);
-          ptx::named_bar_sync(6, 128);             // every frame of the tile has its new residual (re-scores run on any warp)
-          RVQ_TICK(tsub[3]);
+          ptx::named_bar_sync(6, kUpdWarps * 32);  // every frame of the tile has its new residual (re-scores run on any warp)
+          RVQ_TICK(t_bar);
           if (threadIdx.x == 128) { int* qc = reinterpret_cast<int*>(ms + Sm::m_qcnt); qc[0] = 0; qc[1] = 0; }
-          if (s + 1 < p.n_q) {
-            // fp16 operand of the next stage: thread = frame = TMEM lane, 16 dims per store
-            #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              uint32_t w[8];
-              #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float4 v = *reinterpret_cast<const float4*>(rs + rs_off(f, 4 * g + c));
-                w[2 * c] = pack_half2(v.x, v.y);
-                w[2 * c + 1] = pack_half2(v.z, v.w);
-              }
-              ptx::tmem_st8(tq + 64 * X + 8 * g, w);
-            }
-            RVQ_TICK(t_tr);
+          const bool last = s + 1 == p.n_q;
+          float sq = 0.f;
+          if (!last || (TRAIN && p.sqerr != nullptr)) operand_pass<TRAIN>(rs, ms, f, h, tq + 64 * X, !last, sq);
+          RVQ_TICK(t_tr);
+          if (!last) {
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
@@ -640,17 +643,20 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
             RVQ_TICK(t_stw);
           } else {
             if (TRAIN && p.residual_out != nullptr) {
-              // each warp writes its 32 frames, 512 contiguous bytes per frame
-              for (int i = 0; i < 32; ++i) {
-                const int fo = q * 32 + i;
+              // each warp writes 16 frames, 512 contiguous bytes per frame
+              for (int i = 0; i < 16; ++i) {
+                const int fo = q * 32 + h * 16 + i;
                 const int64_t nn = tile_n0 + fo;
                 if (nn < p.N) *reinterpret_cast<float4*>(p.residual_out + nn * 128 + lane * 4) = *reinterpret_cast<const float4*>(rs + rs_off(fo, lane));
               }
-              __syncwarp();
             }
-            if ((jt + 1) * p.n_q < (X ? steps1 : steps0)) next_tile = tile0 + X + 2 * (jt + 1);
+            if ((jt + 1) * p.n_q < (X ? steps1 : steps0)) {
+              next_tile = tile0 + X + 2 * (jt + 1);
+              ptx::named_bar_sync(7, kUpdWarps * 32);   // the other warp of this quadrant may still read these rows
+            }
           }
           if (TRAIN && p.sqerr != nullptr) {
+            if (!(tile_n0 + f < p.N)) sq = 0.f;
             sq = warp_sum(sq);
             if (lane == 0) atomicAdd(&p.sqerr[s], (double)sq);
           }
@@ -664,11 +670,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
       atomicAdd(&p.counters[16], (unsigned long long)t_tr);   atomicAdd(&p.counters[8], (unsigned long long)t_load);
       atomicAdd(&p.counters[20], (unsigned long long)tsub[0]); atomicAdd(&p.counters[21], (unsigned long long)tsub[1]);
       atomicAdd(&p.counters[22], (unsigned long long)tsub[2]); atomicAdd(&p.counters[23], (unsigned long long)tsub[3]);
-      atomicAdd(&p.counters[17], (unsigned long long)t_stw);
+      atomicAdd(&p.counters[17], (unsigned long long)t_stw); atomicAdd(&p.counters[18], (unsigned long long)t_bar);
     }
 #endif
   } else {
-    ptx::reg_inc<232>();
+    ptx::reg_inc<160>();
     // ===== score warps =====
     const int q = warp;                        // TMEM lane quadrant = frames 32q..32q+31 of a tile
     const int f = q * 32 + lane;
@@ -731,10 +737,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
         // |x|^2 of a new tile and the rounding residue of this frame's operand were written by the update warps; the
         // scores above could only exist after they had finished
         float xx = X ? xx_1 : xx_0;
-        if (s == 0) xx = reinterpret_cast<const float*>(ms + Sm::m_xx)[f];
+        if (s == 0) xx = reinterpret_cast<const float*>(ms + Sm::m_cmask)[f] + reinterpret_cast<const float*>(ms + Sm::m_bmask)[f];
         const float xnorm = sqrtf(xx);
         const bool outl = !(xnorm < meta->xlimit);      // also true for NaN
-        const float drn = sqrtf(reinterpret_cast<const float*>(ms + Sm::m_dr2)[f]) * 1.001f;
+        const float drn = sqrtf(reinterpret_cast<const float*>(ms + Sm::m_dr2)[f] + reinterpret_cast<const float*>(ms + Sm::m_dr2)[kM + f]) * 1.001f;
         const float delta = meta->margin_coef * xnorm + meta->margin_dr * drn + meta->margin_abs;
         // ---- candidates: certified winner / up to 4 codes to re-score / mask enumeration / exact scan ----
         float m4[4];
@@ -831,7 +837,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc2_encode_kernel(const TcParam
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc(tmem, 512);
+  if (warp == 13) ptx::tmem_dealloc(tmem, 512);
 }
 
 int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa, int64_t N, int T, int stage0, int n_q,

@@ -33,6 +33,7 @@ for nq in sorted({1, 8, NQ}):
         w = st["warps"]                  # score warps counted = 4 per CTA
         per = lambda k, div: st[k] / div
         print(f"   score warp / tile-stage: wait acc {per('cyc_wait', w)*ctas/ts:.0f}  ld+min {per('cyc_scores', w)*ctas/ts:.0f}  winner {per('cyc_winner', w)*ctas/ts:.0f}  (total per warp {per('cyc_total', w):.0f} cyc)")
-        print(f"   update warp / tile-stage: wait cand {per('cyc_resolve', w)*ctas/ts:.0f}  update {per('cyc_update', w)*ctas/ts:.0f}  operand->tmem {per('cyc_pairbar', w)*ctas/ts:.0f} + st wait {per('tma_late_lat_sum', w)*ctas/ts:.0f}  tile loads (per CTA) {per('cyc_load', w):.0f}")
-        print(f"      update split: wide {per('cand2', w)*ctas/ts:.0f}  own frames {per('cand3_4', w)*ctas/ts:.0f}  lists {per('cand5_8', w)*ctas/ts:.0f}  barrier {per('cand9plus', w)*ctas/ts:.0f}")
+        uw = 2 * w                       # update warps = 8 per CTA
+        print(f"   update warp / tile-stage: wait cand {per('cyc_resolve', uw)*ctas/ts:.0f}  update {per('cyc_update', uw)*ctas/ts:.0f}  operand->tmem {per('cyc_pairbar', uw)*ctas/ts:.0f} + st wait {per('tma_late_lat_sum', uw)*ctas/ts:.0f}  tile loads (per CTA) {per('cyc_load', uw):.0f}")
+        print(f"      update split: setup {per('cand2', uw)*ctas/ts:.0f}  own frames {per('cand3_4', uw)*ctas/ts:.0f}  lists {per('cand5_8', uw)*ctas/ts:.0f}  wide {per('cand9plus', uw)*ctas/ts:.0f}  barrier {per('tma_late_n', uw)*ctas/ts:.0f}")
         print(f"   mma thread / tile-stage: wait A {st['mma_wait_a']/ts:.0f}  wait TMA {st['mma_wait_full']/ts:.0f}  wait acc {st['mma_wait_acc']/ts:.0f}  issue {st['mma_issue']/ts:.0f}  (total per CTA {st['mma_total']/ctas:.0f} cyc)")
