@@ -3,7 +3,6 @@
 
 #include <atomic>
 #include <cstdarg>
-#include <cstdlib>
 
 namespace rvq {
 
@@ -90,9 +89,7 @@ int rvq_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int6
   cudaStream_t st = (cudaStream_t)stream;
   EncodeArgs a{pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, residual_out, stage_sqerr, flags};
   const bool want_tc = tc_shape(K, D) && !(flags & (RVQ_FLAG_FORCE_EXACT | RVQ_FLAG_DIRECT_DIST));
-  if (!want_tc) return simt_encode(a, st);
-  static const int impl = [] { const char* e = getenv("RVQ_TC_IMPL"); return e ? atoi(e) : 2; }();
-  return impl == 1 ? tc_encode(a, st) : tc2_encode(a, st);
+  return want_tc ? tc_encode(a, st) : simt_encode(a, st);
 }
 
 int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int64_t N, int64_t* buckets, void* stream) {
@@ -105,9 +102,6 @@ int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int6
                RVQ_FLAG_DIRECT_DIST | RVQ_FLAG_FORCE_EXACT};
   return simt_encode(a, (cudaStream_t)stream);
 }
-
-/* debug only (not part of the public header): timeline of CTA 0 of the last tcgen05 encode */
-int rvq_debug_trace(long long* out_host, int n) { cudaDeviceSynchronize(); return rvq::tc_debug_trace(out_host, n); }
 
 int rvq_search_stats(const void* pack, uint64_t* out_host, void* stream) {
   if (int e = check_device()) return e;
