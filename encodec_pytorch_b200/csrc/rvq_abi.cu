@@ -103,6 +103,9 @@ int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int6
   return simt_encode(a, (cudaStream_t)stream);
 }
 
+/* debug only (not part of the public header): timeline of CTA 0 of the last tcgen05 encode (RVQ_TC_TRACE builds) */
+int rvq_debug_trace(long long* out_host, int n) { cudaDeviceSynchronize(); return rvq::tc_debug_trace(out_host, n); }
+
 int rvq_search_stats(const void* pack, uint64_t* out_host, void* stream) {
   if (int e = check_device()) return e;
   RVQ_REQUIRE(pack && out_host, "rvq_search_stats: null pointer");

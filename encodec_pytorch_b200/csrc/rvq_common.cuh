@@ -121,5 +121,6 @@ struct EncodeArgs {
 int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st);
 int simt_encode(const EncodeArgs& a, cudaStream_t st);
 int tc_encode(const EncodeArgs& a, cudaStream_t st);    // tcgen05 search, two tiles in flight per CTA (rvq_tc.cu)
+int tc_debug_trace(long long* out_host, int n);         // RVQ_TC_TRACE builds: timeline of CTA 0
 
 }  // namespace rvq

@@ -21,8 +21,8 @@
 //                   rows in flight per quarter-warp), exact fp32 re-score of candidate lists, r <- r - q; then, thread =
 //                   frame, the fp16 operand of the next stage goes to tensor memory (tcgen05.st) together with its
 //                   exact rounding residue; tile loads;
-//            12  TMA producer;  13  MMA issuer (owns the TMEM allocation).
-//            setmaxnreg: 160 registers for the score warps, 152 for the update warps, 48 for the last warpgroup.
+//            12  TMA producer;  13..15  MMA issuers, chunks round-robin (13 owns the TMEM allocation).
+//            setmaxnreg: 152 registers for the score warps, 160 for the update warps, 40 for the last warpgroup.
 //   sync     mbarriers only between roles: a_ready[slot] (update -> MMA), acc_full/acc_empty (MMA <-> score),
 //            cand_ready[slot] (score -> update), full/empty (TMA <-> MMA).
 //
@@ -49,10 +49,6 @@ constexpr int kAccBufs = 3;             // accumulator buffers of kN TMEM column
 constexpr int kTmemA = kAccBufs * kN;   // first TMEM column of the fp16 operands (64 columns per slot)
 constexpr int kThreadsTc = 16 * 32;
 constexpr int kUpdWarps = 8;
-#ifndef RVQ_TC_WIN
-#define RVQ_TC_WIN 3
-#endif
-constexpr int kWin = RVQ_TC_WIN;          // winner rows in flight per quarter-warp
 constexpr int kBig = 5;                 // ncnt marker: more than 4 candidates (enumerate the masks)
 constexpr int kFull = 6;                // ncnt marker: exact scan of the whole table
 constexpr int kRsBytes = kM * 128 * 4;  // fp32 residual of one tile
@@ -83,6 +79,18 @@ static_assert(Sm::total <= 227 * 1024, "shared memory budget");
 static_assert(kTcKPad / 16 == 9 && kN == 128 && kTmemA + 2 * 64 == 512, "operand geometry");
 static_assert((Sm::m_size % 16) == 0 && (Sm::misc % 16) == 0, "alignment");
 
+// debug timeline of CTA 0 (slots 0/1, steps kTraceN0 .. kTraceN0 + kTraceSteps - 1): g_trace[X][step][event] = cycles since kernel start
+constexpr int kTraceSteps = 6, kTraceEv = 16, kTraceN0 = 2;
+__device__ long long g_trace[2 * kTraceSteps * kTraceEv + 128];   // + per-chunk detail of the MMA thread / the producer for (slot 0, step 4)
+#ifdef RVQ_TC_TRACE
+#define RVQ_TRACE(X, n, ev, cond) do { if (blockIdx.x == 0 && (cond) && (n) >= kTraceN0 && (n) < kTraceN0 + kTraceSteps) { \
+    asm volatile("" ::: "memory"); g_trace[(((X) * kTraceSteps) + (n) - kTraceN0) * kTraceEv + (ev)] = clock64() - t_kernel0; asm volatile("" ::: "memory"); } } while (0)
+#define RVQ_TRACE2(X, n, idx) do { if (blockIdx.x == 0 && (X) == 0 && (n) == 4) { \
+    asm volatile("" ::: "memory"); g_trace[2 * kTraceSteps * kTraceEv + (idx)] = clock64() - t_kernel0; asm volatile("" ::: "memory"); } } while (0)
+#else
+#define RVQ_TRACE(X, n, ev, cond) do { } while (0)
+#define RVQ_TRACE2(X, n, idx) do { } while (0)
+#endif
 #ifdef RVQ_TC_TIMERS
 #define RVQ_TICK(acc) do { const unsigned tt_ = (unsigned)clock(); acc += tt_ - tc0; tc0 = tt_; } while (0)
 #define RVQ_TICK0() unsigned tc0 = (unsigned)clock()
@@ -102,9 +110,11 @@ struct TcParams {
 };
 
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
-// residual element group: 16-byte chunk ch (dims 4ch..4ch+3) of frame f, XOR-swizzled so that both
-// "lanes = consecutive chunks of one frame" and "lanes = consecutive frames, one chunk" spread over banks
-__device__ __forceinline__ int rs_off(int f, int ch) { return f * 128 + ((ch ^ (f & 31)) << 2); }
+// residual element group: 16-byte chunk ch (dims 4ch..4ch+3) of frame f, XOR-swizzled with the frame number (its low
+// three bits reversed) so that all three access patterns of the kernel spread over the banks: 8 lanes = 8 consecutive
+// chunks of one frame; 8 lanes = 8 consecutive frames, one chunk; 8 lanes = 2 consecutive frames x 4 consecutive chunks
+__device__ __forceinline__ int rs_swz(int f) { return (f & 24) | ((f & 1) << 2) | (f & 2) | ((f >> 2) & 1); }
+__device__ __forceinline__ int rs_off(int f, int ch) { return f * 128 + ((ch ^ rs_swz(f)) << 2); }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -258,7 +268,7 @@ __device__ __forceinline__ void score_cand(const Cand<NC>& k, const Row4& r, flo
   }
 }
 template <bool TRAIN>
-__device__ __forceinline__ void resolve_wide(const TcParams& p, float* rs, unsigned char* ms, int f, int lane, int s, int rot, int nchunks,
+__device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs, unsigned char* ms, int f, int lane, int s, int rot, int nchunks,
                                              int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn) {
   const int qq = lane >> 3, j = lane & 7;
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
@@ -307,135 +317,108 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, float* rs, unsig
                 bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); }
   }
   const int64_t nfr = tile_n0 + f;
-  if (mine) {
-    apply_row<TRAIN>(p, rs, f, j, r, load_row(t32, bcode, j));     // the winner's row again (rare path; an L1/L2 hit)
-    if (j == 0 && f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
+  if (mine && j == 0) {
+    *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;      // the frame now has a single (exact) winner
+    if (f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
   }
 }
 
 // The residual update of one (slot, stage), executed by the eight update warps (u = 0..7: TMEM lane quadrant q = u & 3,
 // half h = u >> 2 of its 32 frames).
-//   1. frames with wide candidate sets: one frame per warp at a time (resolve_wide);
-//   2. certified frames, branch-free: quarter-warp qq owns frames f0 .. f0+3 (f0 = 32q + 16h + 4qq).  Lane j works on the
-//      16-byte slots 8(i ^ ix) + j (i = 0..3) of each residual row; with the row swizzle of rs_off that slot holds the
-//      logical chunk 8i + (j ^ jx) of the frame, so the winner's row is fetched with its 16-byte pieces permuted by
-//      jx (the 8 lanes of a quarter still cover one contiguous 128-byte segment per i; all addresses are a base +
-//      an immediate).  All
-//      four rows are in flight at once.  A queued frame's slot fetches row 0 and its stores are predicated off;
-//   3. frames with a candidate list (2..4 codes) come from the slot's queue, spread over the 32 quarter-warps:
-//      the four candidate rows are loaded together and re-scored in exact fp32 (core_vq.py:183-187).
+//   1. RESOLVE.  Frames with a candidate list (2..4 codes) come from the slot's queue, spread over the 32 quarter-warps
+//      (8 lanes per frame): the candidate rows are loaded together and scored in exact fp32 (core_vq.py:183-187); frames
+//      with wide candidate sets take a whole warp.  Only the winning code is written back (candidate entry + output).
+//   2. UPDATE + OPERAND.  A group of 4 lanes owns two frames (TMEM lanes g and g + 8 of the warp's 16): lane m holds the
+//      16-byte chunks 4i + m (i = 0..7) of each.  Both winner rows are fetched (64 contiguous bytes per group and i), the
+//      residual row is updated in shared memory (r <- r - q, exact fp32), converted to fp16 with its exact rounding
+//      residue, and the 16 frames x 64 columns of the next stage's operand go to tensor memory with ONE
+//      tcgen05.st.16x256b.x8 -- the register layout of that shape is exactly this lane/chunk assignment, so no
+//      transposition pass and no second barrier are needed.
 template <bool TRAIN>
 __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsigned char* ms, int u, int lane, int s, int rot,
                                             int nchunks, int64_t tile_n0, const float* __restrict__ t32,
-                                            const float* __restrict__ cn, uint32_t (&tsub)[4]) {
-  const int qq = lane >> 3, j = lane & 7;
+                                            const float* __restrict__ cn, uint32_t taddr, bool store, float& sq) {
   const int q = u & 3, h = u >> 2;
-  const int fbase = q * 32 + h * 16;
-  RVQ_TICK0();
   const int* qc = reinterpret_cast<const int*>(ms + Sm::m_qcnt);
   const int nslow = qc[0], nwide = qc[1];
-  const unsigned char* slowq = ms + Sm::m_slowq;
-  const unsigned char* wideq = ms + Sm::m_wideq;
-  const int nv = lane < 16 ? *reinterpret_cast<const int*>(ms + Sm::m_ncnt + (fbase + lane) * 4) : 1;
-  const uint32_t slow = __ballot_sync(0xffffffffu, nv > 1);     // bit i = frame fbase+i is in one of the queues
   const int4* cand = reinterpret_cast<const int4*>(ms + Sm::m_cand);
+  const int g = lane >> 2, m = lane & 3;
+  const int fA = q * 32 + h * 16 + g, fB = fA + 8;
+  if (nslow + nwide > 0) {
+    const int qq = lane >> 3, j = lane & 7;
+    const unsigned char* slowq = ms + Sm::m_slowq;
+    const unsigned char* wideq = ms + Sm::m_wideq;
+    // candidate lists: item qi goes to quarter qi / 8 of warp qi % 8 (the first eight items land on eight different
+    // warps), then qi + 32, ...; a warp none of whose quarters has an item skips the body
+    #pragma unroll 1
+    for (int qi = qq * kUpdWarps + u; qi < ((nslow + 31) & ~31); qi += 32) {
+      const int f = qi < nslow ? int(slowq[qi]) : -1;
+      if (!__any_sync(0xffffffffu, f >= 0)) continue;
+      int4 cd = make_int4(-1, -1, -1, -1);
+      if (f >= 0) cd = cand[f];
+      Cand<4> k;
+      k.c[0] = cd.x; k.c[1] = cd.y; k.c[2] = cd.z; k.c[3] = cd.w;
+      load_cand<4>(k, j, t32, cn);
+      Row4 r;
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f >= 0) r = load_res(rs, f, j);
+      const float rr = quarter_sum(dot_row(r, r));
+      // core_vq.py:183-187, lowest index on ties; NaN distances: keep the first candidate unless a finite one exists
+      float best = inf_f(); int bcode = 0x7fffffff, bidx = 0;
+      score_cand<4>(k, r, rr, best, bcode, bidx);
+      if (bcode == 0x7fffffff) bcode = cd.x;
+      const int64_t nfr = tile_n0 + f;
+      if (f >= 0 && j == 0) {
+        *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;
+        if (f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
+      }
+    }
+    // wide candidate sets: one frame per warp at a time, handed out from the last warp down
+    #pragma unroll 1
+    for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
+  }
+  if (nslow + nwide > 0) ptx::named_bar_sync(6, kUpdWarps * 32);      // every listed / wide frame of the tile has its winner
+  // both winner rows in flight
+  float4 qa[8], qb[8];
   {
-    const int f0 = fbase + 4 * qq;
-    const int ix = 2 * h + (qq >> 1), jx0 = 4 * (qq & 1);
-    // physical slot 8(i ^ ix) + j of frame f0 + k holds the logical chunk 8i + (j ^ (jx0 + k)): four shared-memory bases
-    // (one per i) + immediates on the residual side, one row pointer per frame + immediates on the table side
-    float* rb[4];
+    const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
+    const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
     #pragma unroll
-    for (int i = 0; i < 4; ++i) rb[i] = rs + f0 * 128 + 32 * (i ^ ix) + 4 * j;
-    int oc[4];
+    for (int i = 0; i < 8; ++i) qa[i] = __ldg(ra + 4 * i);
     #pragma unroll
-    for (int k = 0; k < 4; ++k) oc[k] = ((slow >> (4 * qq + k)) & 1u) ? -1 : cand[f0 + k].x;
-    // a rolling window of kWin rows in flight: the buffer of frame k is refilled with the row of frame k + kWin
-    Row4 buf[kWin];
-    auto fetch = [&](int k) {
-#ifdef RVQ_EXP_ROW0       // experiment (wrong results): every gather hits the same L1-resident row
-      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(oc[k] >= 0 ? 0 : 0) * 128 + 4 * (j ^ (jx0 + k)));
-#else
-      const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(oc[k] >= 0 ? oc[k] : 0) * 128 + 4 * (j ^ (jx0 + k)));
-#endif
-      #pragma unroll
-      for (int i = 0; i < 4; ++i) buf[k % kWin].v[i] = __ldg(rp + 8 * i);
-    };
-    #pragma unroll
-    for (int k = 0; k < kWin; ++k) fetch(k);
-    RVQ_TICK(tsub[0]);
-    #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float4 r[4];
-      #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = *reinterpret_cast<const float4*>(rb[i] + k * 128);
-      #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 n = sub_row<TRAIN>(p, r[i], buf[k % kWin].v[i]);
-        if (oc[k] >= 0) *reinterpret_cast<float4*>(rb[i] + k * 128) = n;
-      }
-      if (k + kWin < 4) fetch(k + kWin);
-    }
+    for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
   }
-  RVQ_TICK(tsub[1]);
-  // candidate lists: item qi goes to quarter qi / 8 of warp qi % 8 (the first eight items land on eight different
-  // warps), then qi + 32, ...; a warp none of whose quarters has an item skips the body
-  const int gq = qq * kUpdWarps + u;
-  #pragma unroll 1
-  for (int qi = gq; qi < ((nslow + 31) & ~31); qi += 32) {
-    const int f = qi < nslow ? int(slowq[qi]) : -1;
-    if (!__any_sync(0xffffffffu, f >= 0)) continue;
-    int4 cd = make_int4(-1, -1, -1, -1);
-    if (f >= 0) cd = cand[f];
-    Cand<4> k;
-    k.c[0] = cd.x; k.c[1] = cd.y; k.c[2] = cd.z; k.c[3] = cd.w;
-    load_cand<4>(k, j, t32, cn);
-    Row4 r;
+  uint32_t w[32];
+  float e2a, e2b;
+  auto process = [&](int f, const float4 (&qr)[8], int half, float& e2) {
+    const int sw = rs_swz(f);
+    float* rbase = rs + f * 128 + ((m ^ (sw & 3)) << 2);
+    float e[4] = {0.f, 0.f, 0.f, 0.f};
+    float sqf = 0.f;
     #pragma unroll
-    for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (f >= 0) r = load_res(rs, f, j);
-    const float rr = quarter_sum(dot_row(r, r));
-    // core_vq.py:183-187, lowest index on ties; NaN distances: keep the first candidate unless a finite one exists
-    float best = inf_f(); int bcode = 0x7fffffff, bidx = 0;
-    score_cand<4>(k, r, rr, best, bcode, bidx);
-    if (bcode == 0x7fffffff) bcode = cd.x;
-    const int64_t nfr = tile_n0 + f;
-    if (f >= 0) {
-      #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 a01 = bidx == 1 ? k.w[1].v[i] : k.w[0].v[i], a23 = bidx == 3 ? k.w[3].v[i] : k.w[2].v[i];
-        *reinterpret_cast<float4*>(rs + rs_off(f, 8 * i + j)) = sub_row<TRAIN>(p, r.v[i], bidx >= 2 ? a23 : a01);
-      }
-      if (j == 0 && f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
+    for (int i = 0; i < 8; ++i) {
+      float4* rp = reinterpret_cast<float4*>(rbase + ((i ^ (sw >> 2)) << 4));
+      const float4 n = sub_row<TRAIN>(p, *rp, qr[i]);
+      *rp = n;
+      e[i & 3] = residue2(n.x, n.y, w[4 * i + 2 * half], e[i & 3]);
+      e[i & 3] = residue2(n.z, n.w, w[4 * i + 2 * half + 1], e[i & 3]);
+      if (TRAIN) sqf = dot4(n, n, sqf);
     }
+    e2 = (e[0] + e[1]) + (e[2] + e[3]);
+    if (TRAIN && f < p.tf && tile_n0 + f < p.N) sq += sqf;      // sum((q - r)^2) of core_vq.py:319 = |new residual|^2
+  };
+  process(fA, qa, 0, e2a);
+  process(fB, qb, 1, e2b);
+  // exact rounding residue of the new operand rows: sum over the 4 lanes of the group
+  e2a += __shfl_xor_sync(0xffffffffu, e2a, 1); e2b += __shfl_xor_sync(0xffffffffu, e2b, 1);
+  e2a += __shfl_xor_sync(0xffffffffu, e2a, 2); e2b += __shfl_xor_sync(0xffffffffu, e2b, 2);
+  if (m == 0) {
+    float* dr2 = reinterpret_cast<float*>(ms + Sm::m_dr2);
+    dr2[fA] = e2a; dr2[kM + fA] = 0.f;
+    dr2[fB] = e2b; dr2[kM + fB] = 0.f;
   }
-  RVQ_TICK(tsub[2]);
-  // frames with wide candidate sets: one frame per warp at a time, handed out from the last warp down (the candidate
-  // lists start at the first)
-  #pragma unroll 1
-  for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
-  RVQ_TICK(tsub[3]);
-}
-
-// Thread = frame = TMEM lane (f = 32q + lane), dims 64h .. 64h+63 of the new residual: fp16 operand of the next stage
-// to tensor memory (16 dims per tcgen05.st), its exact squared rounding residue |r - fp16(r)|^2 (it enters the score
-// margin of the next stage) and, in training, the squared-error partial sum((q - r)^2) = |new residual|^2 (core_vq.py:319).
-template <bool TRAIN>
-__device__ __forceinline__ void operand_pass(const float* rs, unsigned char* ms, int f, int h, uint32_t taddr, bool store, float& sq) {
-  float e[4] = {0.f, 0.f, 0.f, 0.f};
-  #pragma unroll 2
-  for (int g = 0; g < 4; ++g) {
-    uint32_t w[8];
-    #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(rs + rs_off(f, 16 * h + 4 * g + c));
-      e[c] = residue2(v.x, v.y, w[2 * c], e[c]);
-      e[c] = residue2(v.z, v.w, w[2 * c + 1], e[c]);
-      if (TRAIN) sq = dot4(v, v, sq);
-    }
-    if (store) ptx::tmem_st8(taddr + 32 * h + 8 * g, w);
-  }
-  reinterpret_cast<float*>(ms + Sm::m_dr2)[h * kM + f] = (e[0] + e[1]) + (e[2] + e[3]);
+  if (store) ptx::tmem_st_16x256b_x8(taddr, w);
 }
 
 }  // namespace
@@ -480,9 +463,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+#ifdef RVQ_TC_TRACE
+  __shared__ long long s_t0;
+  if (threadIdx.x == 0) s_t0 = clock64();
+  __syncthreads();
+  const long long t_kernel0 = s_t0;
+#endif
 
   if (warp >= 12) {
-    ptx::reg_dec<48>();
+    ptx::reg_dec<40>();
     if (warp == 12) {
       // ===== TMA producer: the three K-thirds of every 128-code chunk, in the global step order.  One thread: the slots
       // come free in the order they were filled, and a spinning warp costs the working warps of its scheduler issue slots =====
@@ -507,61 +496,61 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         }
       }
       __syncwarp();
-    } else if (warp == 13) {
-      // ===== MMA issuer: per chunk 8 MMAs with A from tensor memory + 1 with the constant shared-memory block =====
-      if (lane == 0) {
+    } else {
+      // ===== MMA issuers: per chunk 8 MMAs with A from tensor memory + 1 with the constant shared-memory block.  The
+      // issue path of ONE thread (4 barrier waits, 9 MMAs, 4 commits, next to three other warps on its scheduler) takes
+      // ~1400 cycles per chunk against 576 tensor cycles, so the chunks of the global order go round-robin to three
+      // issuer warps; issuer `who` therefore always fills accumulator buffer `who`. =====
+      // The loop is warp-uniform (every lane waits and computes the same descriptors; one elected lane issues), so the
+      // operands of tcgen05.mma stay in uniform registers.
+      {
         constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
+        const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem);      // a provably warp-uniform copy (uniform register)
         const uint64_t ad_aug = ptx::umma_desc_kmajor_noswz(sbase + Sm::aug, 2048, 128);
         const uint64_t bd0 = ptx::umma_desc_kmajor_noswz(sbase + Sm::ring, kTcLBO, kTcSBO);
-#ifdef RVQ_TC_TIMERS
-        uint32_t m_wa = 0, m_wf = 0, m_wc = 0, m_is = 0; const long long m_t0 = clock64();
-#endif
-        uint32_t slot = 0, ph = 0, buf = 0, bph = 0;      // ring slot / phase of the next K-third, accumulator buffer / phase
+        const uint32_t who = uint32_t(warp - 13);
+        const uint32_t d_tmem = tmem_u + who * kN;
+        const uint32_t bar_accf = ptx::smem_u32(&bars->acc_full[who]), bar_acce = ptx::smem_u32(&bars->acc_empty[who]);
+        uint32_t gi = 0, bph = 0;              // global chunk index, phase of this issuer's accumulator buffer
         for (int n = 0; n < steps0; ++n) {
           for (int X = 0; X < 2; ++X) {
             if (X == 1 && n >= steps1) break;
-            RVQ_TICK0();
             ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[X]), uint32_t(n) & 1);       // fp16 operand of this step is in TMEM
             ptx::tc_fence_after();
-            RVQ_TICK(m_wa);
-            const uint32_t a_tmem = tmem + kTmemA + 64 * X;
-            for (int c = 0; c < nchunks; ++c) {
-              ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), bph ^ 1);                     // accumulator drained
-              RVQ_TICK(m_wc);
-              const uint32_t d_tmem = tmem + buf * kN;
+            RVQ_TRACE(X, n, 0, who == 0 && lane == 0);
+            const uint32_t a_tmem = tmem_u + kTmemA + 64 * X;
+            for (int c = 0; c < nchunks; ++c, ++gi) {
+              if (gi % kAccBufs != who) continue;
+              ptx::mbar_wait(bar_acce, bph ^ 1);                                                 // accumulator drained
+              bph ^= 1;
+              if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 0);
               #pragma unroll
               for (int h = 0; h < 3; ++h) {
+                const uint32_t t3 = 3 * gi + h, slot = t3 % kRing, ph = (t3 / kRing) & 1;
                 ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), ph);                            // K-third landed
                 ptx::tc_fence_after();
-                RVQ_TICK(m_wf);
+                if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 1 + h);
                 const uint64_t bs = bd0 + uint64_t((slot * kSlotBytes) >> 4);
                 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                   const uint64_t bk = bs + uint64_t((k * 2 * kTcLBO) >> 4);
-                  if (h == 2 && k == 2) ptx::umma_f16_ss(d_tmem, ad_aug, bk, idesc, 1u);
-                  else ptx::umma_f16_ts(d_tmem, a_tmem + 8 * (3 * h + k), bk, idesc, (h | k) ? 1u : 0u);
+                  if (h == 2 && k == 2) ptx::umma_f16_ss_w(d_tmem, ad_aug, bk, idesc, 1u);
+                  else ptx::umma_f16_ts_w(d_tmem, a_tmem + 8 * (3 * h + k), bk, idesc, (h | k) ? 1u : 0u);
                 }
-                ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));   // ring slot reusable once read
-                if (++slot == kRing) { slot = 0; ph ^= 1; }
-                RVQ_TICK(m_is);
+                ptx::umma_commit_w(ptx::smem_u32(&bars->empty[slot]));   // ring slot reusable once read
               }
-              ptx::umma_commit(ptx::smem_u32(&bars->acc_full[buf]));   // scores ready for the score warps
-              if (++buf == kAccBufs) { buf = 0; bph ^= 1; }
+              ptx::umma_commit_w(bar_accf);                              // scores ready for the score warps
+              if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 4);
+              if (c == 0) RVQ_TRACE(X, n, 1, lane == 0);
             }
+            RVQ_TRACE(X, n, 2, lane == 0 && who == (gi + kAccBufs - 1) % kAccBufs);
           }
         }
-#ifdef RVQ_TC_TIMERS
-        if (p.counters != nullptr) {
-          atomicAdd(&p.counters[11], (unsigned long long)m_wa); atomicAdd(&p.counters[12], (unsigned long long)m_wf);
-          atomicAdd(&p.counters[13], (unsigned long long)m_wc); atomicAdd(&p.counters[14], (unsigned long long)(clock64() - m_t0));
-          atomicAdd(&p.counters[19], (unsigned long long)m_is);
-        }
-#endif
       }
       __syncwarp();
     }
   } else if (warp >= 4) {
-    ptx::reg_inc<152>();
+    ptx::reg_inc<160>();
     // ===== update warps =====
     const int u = warp - 4;
     const int q = u & 3, h = u >> 2;           // TMEM lane quadrant (frames 32q..32q+31 of a tile), half of the dims / of the frames
@@ -570,7 +559,6 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
 #ifdef RVQ_TC_TIMERS
     uint32_t t_wait = 0, t_upd = 0, t_tr = 0, t_load = 0, t_stw = 0, t_bar = 0;
 #endif
-    uint32_t tsub[4] = {0u, 0u, 0u, 0u};     // (timers) wide sets / own frames / candidate lists / barrier
     // load dims 64h..64h+63 of the latent tile `tile` into slot X: fp32 residual rows, |x|^2, fp16 operand in tensor
     // memory, rounding residue
     auto load_tile = [&](int X, int tile) {
@@ -629,24 +617,26 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           if (u == 0) ptx::mbar_wait(ptx::smem_u32(&bars->cand_ready[X]), uint32_t(n) & 1);
           ptx::named_bar_sync(8, kUpdWarps * 32);
           RVQ_TICK(t_wait);
-          update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st), tsub);
-          RVQ_TICK(t_upd);
-          ptx::named_bar_sync(6, kUpdWarps * 32);  // every frame of the tile has its new residual (re-scores run on any warp)
-          RVQ_TICK(t_bar);
-          if (threadIdx.x == 128) { int* qc = reinterpret_cast<int*>(ms + Sm::m_qcnt); qc[0] = 0; qc[1] = 0; }
+          RVQ_TRACE(X, n, 6, u == 0 && lane == 0);
           const bool last = s + 1 == p.n_q;
           float sq = 0.f;
-          if (!last || (TRAIN && p.sqerr != nullptr)) operand_pass<TRAIN>(rs, ms, f, h, tq + 64 * X, !last, sq);
-          RVQ_TICK(t_tr);
+          // operand rows of this warp: TMEM lanes 32q + 16h .. +15, columns of slot X
+          update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st),
+                             tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, sq);
+          RVQ_TICK(t_upd);
+          RVQ_TRACE(X, n, 7, u == 0 && lane == 0);
+          if (threadIdx.x == 128) { int* qc = reinterpret_cast<int*>(ms + Sm::m_qcnt); qc[0] = 0; qc[1] = 0; }
           if (!last) {
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[X]));
             RVQ_TICK(t_stw);
+            RVQ_TRACE(X, n, 8, u == 0 && lane == 0);
           } else {
             if (TRAIN && p.residual_out != nullptr) {
-              // each warp writes 16 frames, 512 contiguous bytes per frame
+              // each warp writes the 16 frames it has just updated, 512 contiguous bytes per frame
+              __syncwarp();
               for (int i = 0; i < 16; ++i) {
                 const int fo = q * 32 + h * 16 + i;
                 const int64_t nn = tile_n0 + fo;
@@ -659,7 +649,6 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
             }
           }
           if (TRAIN && p.sqerr != nullptr) {
-            if (!(f < p.tf && tile_n0 + f < p.N)) sq = 0.f;
             sq = warp_sum(sq);
             if (lane == 0) atomicAdd(&p.sqerr[s], (double)sq);
           }
@@ -671,13 +660,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     if (lane == 0 && p.counters != nullptr) {
       atomicAdd(&p.counters[15], (unsigned long long)t_wait); atomicAdd(&p.counters[7], (unsigned long long)t_upd);
       atomicAdd(&p.counters[16], (unsigned long long)t_tr);   atomicAdd(&p.counters[8], (unsigned long long)t_load);
-      atomicAdd(&p.counters[20], (unsigned long long)tsub[0]); atomicAdd(&p.counters[21], (unsigned long long)tsub[1]);
-      atomicAdd(&p.counters[22], (unsigned long long)tsub[2]); atomicAdd(&p.counters[23], (unsigned long long)tsub[3]);
       atomicAdd(&p.counters[17], (unsigned long long)t_stw); atomicAdd(&p.counters[18], (unsigned long long)t_bar);
     }
 #endif
   } else {
-    ptx::reg_inc<160>();
+    ptx::reg_inc<152>();
     // ===== score warps =====
     const int q = warp;                        // TMEM lane quadrant = frames 32q..32q+31 of a tile
     const int f = q * 32 + lane;
@@ -714,6 +701,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), aph);
           ptx::tc_fence_after();
           RVQ_TICK(t_wait);
+          if (c == 0) RVQ_TRACE(X, n, 3, warp == 0 && lane == 0);
+          if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c);
           uint32_t v0[32], v1[32];
           ptx::tmem_ld32(tlane + buf * kN, v0);
           ptx::tmem_ld32(tlane + buf * kN + 32, v1);
@@ -731,12 +720,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));
+          if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c + 1);
           #pragma unroll
           for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
           bmin[30] = min32(v0);
           bmin[31] = min32(v1);
           RVQ_TICK(t_epi);
+          if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c + 2);
         }
+        RVQ_TRACE(X, n, 4, warp == 0 && lane == 0);
         // |x|^2 of a new tile and the rounding residue of this frame's operand were written by the update warps; the
         // scores above could only exist after they had finished
         float xx = X ? xx_1 : xx_0;
@@ -814,6 +806,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         if (X) xx_1 = xx; else xx_0 = xx;
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->cand_ready[X]));    // winners and queues visible to the update warps
+        RVQ_TRACE(X, n, 5, warp == 0 && lane == 0);
         RVQ_TICK(t_win);
       }
     }
@@ -841,6 +834,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 13) ptx::tmem_dealloc(tmem, 512);
+}
+
+int tc_debug_trace(long long* out_host, int n) {
+  const int m = n < 2 * kTraceSteps * kTraceEv + 128 ? n : 2 * kTraceSteps * kTraceEv + 128;
+  RVQ_CUDA(cudaMemcpyFromSymbol(out_host, g_trace, size_t(m) * sizeof(long long)));
+  return m;
 }
 
 int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa, int64_t N, int T, int stage0, int n_q,
