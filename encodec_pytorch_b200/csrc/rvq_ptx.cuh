@@ -169,6 +169,43 @@ __device__ __forceinline__ void umma_commit_w(uint32_t bar) {
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
+// One K-third of a 128-code chunk in a single statement (one election): three K=16 MMAs whose A operands sit 8 TMEM
+// columns apart and whose B descriptors sit `kstep16` (bytes >> 4) apart, then the commit that frees the ring slot.
+// `accumulate` == 0: the first MMA overwrites the accumulator.
+__device__ __forceinline__ void umma_third_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t bar_empty) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, t;\n\t.reg .b64 b1, b2;\n\t.reg .b32 a1, a2;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\t"
+      "add.s64 b1, %2, 256;\n\tadd.s64 b2, %2, 512;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(bar_empty)
+      : "memory");
+}
+// Last K-third: two MMAs with A from tensor memory, the augmented MMA with A from shared memory (a_desc), the commit
+// that frees the ring slot and the commit that publishes the accumulator.
+__device__ __forceinline__ void umma_third_last_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t bar_empty, uint32_t bar_acc) {
+  asm volatile(
+      "{\n\t.reg .pred e, t;\n\t.reg .b64 b1, b2;\n\t.reg .b32 a1;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.u32 a1, %1, 8;\n\t"
+      "add.s64 b1, %3, 256;\n\tadd.s64 b2, %3, 512;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %4, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %4, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, b2, %4, t;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(bar_empty), "r"(bar_acc)
+      : "memory");
+}
 // all MMAs issued so far by this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -531,15 +531,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
                 ptx::tc_fence_after();
                 if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 1 + h);
                 const uint64_t bs = bd0 + uint64_t((slot * kSlotBytes) >> 4);
-                #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                  const uint64_t bk = bs + uint64_t((k * 2 * kTcLBO) >> 4);
-                  if (h == 2 && k == 2) ptx::umma_f16_ss_w(d_tmem, ad_aug, bk, idesc, 1u);
-                  else ptx::umma_f16_ts_w(d_tmem, a_tmem + 8 * (3 * h + k), bk, idesc, (h | k) ? 1u : 0u);
-                }
-                ptx::umma_commit_w(ptx::smem_u32(&bars->empty[slot]));   // ring slot reusable once read
+                static_assert(((2 * kTcLBO) >> 4) == 256, "B descriptor step of one K=16 MMA");
+                if (h < 2) ptx::umma_third_ts_w(d_tmem, a_tmem + 24 * h, bs, idesc, h == 0 ? 0u : 1u, ptx::smem_u32(&bars->empty[slot]));
+                else ptx::umma_third_last_w(d_tmem, a_tmem + 48, ad_aug, bs, idesc, ptx::smem_u32(&bars->empty[slot]), bar_accf);
               }
-              ptx::umma_commit_w(bar_accf);                              // scores ready for the score warps
               if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 4);
               if (c == 0) RVQ_TRACE(X, n, 1, lane == 0);
             }
@@ -874,6 +869,7 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   const int64_t passes = (N + per_round - 1) / per_round;
   int64_t tf = (N + 2ll * sm_count * passes - 1) / (2ll * sm_count * passes);
   tf = tf < 16 ? 16 : (tf > kM ? kM : tf);
+  tf = kM;   // measured on B200 (cfg2): full 128-frame tiles with a single-tile tail beat balanced 82-frame tiles (0.62 vs 0.67 ms)
   if (const char* e = getenv("RVQ_TC_TILE_FRAMES")) { const int v = atoi(e); if (v >= 1 && v <= kM) tf = v; }   // tuning knob
   p.tf = int(tf);
   const int64_t ntiles = (N + tf - 1) / tf;
