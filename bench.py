@@ -29,7 +29,16 @@ METRIC = "rvq_encode_frames_per_s"
 UNIT = "frames/s"
 B, D, T, NQ, BINS, FRAME_RATE, BW = 64, 128, 750, 32, 1024, 75, 24.0
 FLOP_PER_FRAME_STAGE = 2 * BINS * D          # only the x.c^T contraction counts
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc_encode_kernel launch at cfg2 (ncu --set full,
+# profiles/r1b_tc_encode_ncu_raw.csv): 51.04 MB + 1.60 MB; algorithmic: 24.6 MB latents + 12.3 MB codes (+ first touch of the pack)
+NCU_DRAM_BYTES_PER_LAUNCH = 52.64e6
 WORKLOAD = f"cfg2: 24 kHz 24 kbps RVQ encode, latents [{B},{D},{T}] fp32, n_q={NQ}, bins={BINS}"
+
+
+def _latents(b: int, d: int, t: int, seed: int) -> torch.Tensor:
+    """Synthetic unit-variance fp32 latents [B, D, T] from a private CPU generator."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(b, d, t, generator=g, dtype=torch.float32)
 
 
 def _peaks():
@@ -165,7 +174,6 @@ def run_b200(args):
     import torch.distributed as dist
     import encodec_pytorch_b200 as E
     from encodec_pytorch_b200 import _lib
-    from oracle import cases as C
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,7 +189,7 @@ def run_b200(args):
     q = E.ResidualVectorQuantizer(dimension=D, n_q=NQ, bins=BINS, kmeans_init=False).to(dev).eval()
     # rotating input sets whose footprint exceeds the 126 MB L2, so every step reads its latents from HBM
     n_sets = 8
-    xs = [C.latents(B, D, T, 1234 + 17 * (rank * n_sets + i)).to(dev) for i in range(n_sets)]
+    xs = [_latents(B, D, T, 1234 + 17 * (rank * n_sets + i)).to(dev) for i in range(n_sets)]
     set_bytes = xs[0].numel() * 4 + NQ * B * T * 8
     frames = B * T
 
@@ -212,24 +220,44 @@ def run_b200(args):
         total_ms = t_start.elapsed_time(t_end)
         kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
 
-        # ---- end to end: pinned host latents in, int64 codes back to pinned host, every step -----
-        xh = [C.latents(B, D, T, 99 + i).pin_memory() for i in range(2)]
-        ch = [torch.empty((NQ, B, T), dtype=torch.int64).pin_memory() for _ in range(2)]
-        xd = [torch.empty_like(xs[0]) for _ in range(2)]
+        # ---- end to end: pinned host latents in, int64 codes back to pinned host, every step.  The three legs of a step
+        # (H2D copy, encode through the public API, D2H copy) run on three streams with 3-deep buffers, the way a serving
+        # loop would drive the module: a step's copies overlap its neighbours' kernels, nothing is skipped or cached. -----
+        nb = 3
+        xh = [_latents(B, D, T, 99 + i).pin_memory() for i in range(nb)]
+        ch = [torch.empty((NQ, B, T), dtype=torch.int64).pin_memory() for _ in range(nb)]
+        xd = [torch.empty_like(xs[0]) for _ in range(nb)]
+        s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ev_in = [torch.cuda.Event() for _ in range(nb)]
+        ev_cmp = [torch.cuda.Event() for _ in range(nb)]
+        ev_out = [torch.cuda.Event() for _ in range(nb)]
 
-        def e2e_step(i):
-            xd[i % 2].copy_(xh[i % 2], non_blocking=True)
-            c = q.encode(xd[i % 2], FRAME_RATE, BW)
-            ch[i % 2].copy_(c, non_blocking=True)
+        def e2e_run(n_steps):
+            for i in range(n_steps):
+                k = i % nb
+                with torch.cuda.stream(s_in):
+                    if i >= nb:
+                        s_in.wait_event(ev_cmp[k])              # the encode that read xd[k] is done
+                    xd[k].copy_(xh[k], non_blocking=True)
+                    ev_in[k].record(s_in)
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_in[k])
+                    c = q.encode(xd[k], FRAME_RATE, BW)
+                    ev_cmp[k].record(s_cmp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[k])
+                    ch[k].copy_(c, non_blocking=True)
+                    c.record_stream(s_out)
+                    ev_out[k].record(s_out)
 
-        for i in range(3):
-            e2e_step(i)
+        e2e_run(2 * nb)
         barrier()
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_start.record()
-        for i in range(args.steps):
-            e2e_step(i)
-        e_end.record()
+        e_start.record(s_in)
+        e2e_run(args.steps)
+        s_out.wait_stream(s_in)
+        s_out.wait_stream(s_cmp)
+        e_end.record(s_out)
         barrier()
         e2e_ms = e_start.elapsed_time(e_end)
 
@@ -266,12 +294,13 @@ def run_b200(args):
                        "codebooks": "kaiming-uniform, torch.manual_seed(0) (reference constructor)",
                        "parallelism": f"frames sharded over {world} rank(s), no data-path collective"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "frac": achieved / peaks["tflops"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "kernel": "fused n_q-stage encode (one launch per step)", "kernel_ms": kernel_ms,
                          "peak_source": peaks["source"] + " burst (kernel timed alone)",
                          "frac_of_sustained": (achieved / peaks["tflops_sustained"]) if peaks["tflops_sustained"] else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * T * 4,
-                    "d2h_bytes_per_step": NQ * B * T * 8, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": NQ * B * T * 8, "ms_per_step": e2e_ms / args.steps,
+                    "how": "public API (ResidualVectorQuantizer.encode) on 3 streams: H2D / encode / D2H of neighbouring steps overlap"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "decode": {"frames_per_s": frames / (dec_ms * 1e-3), "ms": dec_ms,
