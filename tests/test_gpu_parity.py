@@ -370,3 +370,62 @@ def test_single_layer_and_codebook_api():
         qq, ii = cb(xin)
         assert torch.equal(ii, ind) and torch.equal(qq, dq.permute(0, 2, 1))
         assert torch.equal(layer.codebook, cb.embed)
+
+
+# ---- full-size property tests (BASELINE.json configs[1] and a many-tiles-per-SM case) ----------------------
+def _teacher_forced_on_gpu(q, x, codes, rel_gap=1e-6):
+    """Stage by stage, on the kernel's own residual chain: the code of stage s must be the fp32 argmin of the
+    exact SIMT search given the residual rebuilt from codes[:s] (gathers + ordered fp32 subtractions, the
+    arithmetic of core_vq.py:357-367); a difference is accepted only at an fp64 near-tie (< rel_gap relative)."""
+    from encodec_pytorch_b200 import _ops as ops, _lib as L
+    pk = q.vq._stack_pack()
+    n_q, B, T = codes.shape
+    res = x.transpose(1, 2).contiguous().clone()               # [B, T, D]
+    mismatch = near = 0
+    for s in range(n_q):
+        emb = q.vq.layers[s]._codebook.embed
+        want = ops.encode(pk, res.transpose(1, 2), s, 1, flags=L.FLAG_FORCE_EXACT)[0][0]      # [B, T]
+        got = codes[s]
+        bad = (want != got).nonzero()
+        mismatch += int(bad.shape[0])
+        if bad.shape[0]:
+            r = res[bad[:, 0], bad[:, 1]].double()
+            dg = ((r - emb[got[bad[:, 0], bad[:, 1]]].double()) ** 2).sum(-1)
+            dw = ((r - emb[want[bad[:, 0], bad[:, 1]]].double()) ** 2).sum(-1)
+            gap = (dg - dw).abs() / torch.maximum(dw.abs(), torch.full_like(dw, 1e-30))
+            assert bool((gap < rel_gap).all()), f"stage {s}: {int((gap >= rel_gap).sum())} codes differ beyond a near-tie"
+            near += int(bad.shape[0])
+        res = res - emb[got]                                    # the kernel's r <- r - q (exact fp32)
+    return mismatch, near, res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 750, 32), (5, 18944, 4), (1, 130, 32)],
+                         ids=["cfg2_48000x32", "five_tiles_per_sm_x4", "two_tiles_x32"])
+def test_full_size_properties(shape):
+    """Size-independent properties at BASELINE.json's full size: every code is the exact-search argmin on the
+    kernel's own residual chain (near-ties excepted), decode(codes) + final residual reproduces the input, and
+    the launch is deterministic."""
+    import encodec_pytorch_b200 as E
+    from encodec_pytorch_b200 import _ops as ops
+    B, T, n_q = shape
+    torch.manual_seed(0)
+    q = E.ResidualVectorQuantizer(dimension=128, n_q=n_q, bins=1024, kmeans_init=False).cuda().eval()
+    x = C.latents(B, 128, T, 4321).cuda()
+    with torch.no_grad():
+        codes = q.encode(x, 75, None)
+        codes2 = q.encode(x, 75, None)
+        assert codes.shape == (n_q, B, T) and codes.dtype == torch.int64
+        assert torch.equal(codes, codes2), "the search must be deterministic"
+        assert int(codes.min()) >= 0 and int(codes.max()) < 1024
+        mismatch, near, res = _teacher_forced_on_gpu(q, x, codes)
+        assert near <= max(2, 2e-3 * codes.numel() / n_q), (mismatch, near)
+        # decode (ordered sum of the gathered rows) + residual chain == input, to fp32 summation-order noise
+        dec = q.decode(codes)                                   # [B, D, T]
+        err = (dec + res.transpose(1, 2) - x).abs().max().item()
+        assert err <= 1e-4, err
+        # the kernel's own residual output agrees with the rebuilt chain bit for bit
+        pk = q.vq._stack_pack()
+        c3, _, _, r3 = ops.encode(pk, x, 0, n_q, want_residual=True)
+        assert torch.equal(c3, codes)
+        assert torch.equal(r3, res)
