@@ -475,7 +475,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     if (warp == 12) {
       // ===== TMA producer: the three K-thirds of every 128-code chunk, in the global step order.  One thread: the slots
       // come free in the order they were filled, and a spinning warp costs the working warps of its scheduler issue slots =====
-      if (lane == 0) {
+      // (warp-uniform loop, elected issue: the copy's operands stay in uniform registers)
+      {
         uint32_t slot = 0, ph = 0;             // ring position of the next K-third
         for (int n = 0; n < steps0; ++n) {
           for (int X = 0; X < 2; ++X) {
@@ -486,9 +487,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
               #pragma unroll 1
               for (int third = 0; third < 3; ++third) {
                 ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), ph ^ 1);
-                const uint32_t fb = ptx::smem_u32(&bars->full[slot]);
-                ptx::mbar_expect_tx(fb, kSlotBytes);
-                ptx::bulk_g2s(sbase + Sm::ring + slot * kSlotBytes, img + size_t(pc) * kTcChunkBytes + third * kSlotBytes, kSlotBytes, fb);
+                ptx::bulk_g2s_expect_w(sbase + Sm::ring + slot * kSlotBytes, img + size_t(pc) * kTcChunkBytes + third * kSlotBytes,
+                                       kSlotBytes, ptx::smem_u32(&bars->full[slot]));
                 if (++slot == kRing) { slot = 0; ph ^= 1; }
               }
             }

@@ -29,6 +29,6 @@ base = 2 * STEPS * EV
 print("MMA thread, slot 0 step 4, per chunk: acc free | third0 landed | third1 | third2 | all issued")
 for c in range(8):
     print(f"  chunk {c}: " + "  ".join(str(arr[base + 8 * c + e]) for e in range(5)))
-print("score warp 0, slot 0 step 4, per chunk: acc_full seen | accumulator released | minima done")
-for c in range(8):
-    print(f"  chunk {c}: " + "  ".join(str(arr[base + 64 + 3 * c + e]) for e in range(3)))
+print("update warps, slot 0 step 4: start | lists done | wide done | barrier | rows requested | frame A done | frame B done | operand stored")
+for u in range(8):
+    print(f"  warp {u}: " + "  ".join(str(arr[base + 64 + 8 * u + e]) for e in range(8)))
