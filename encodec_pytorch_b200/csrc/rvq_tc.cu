@@ -524,16 +524,23 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
               ptx::mbar_wait(bar_acce, bph ^ 1);                                                 // accumulator drained
               bph ^= 1;
               if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 0);
+              // the three K-thirds of the chunk first (in steady state they have landed long ago), then all nine MMAs
+              // back to back: the chunk then completes one MMA time after its accumulator came free
+              uint32_t slot[3];
               #pragma unroll
               for (int h = 0; h < 3; ++h) {
-                const uint32_t t3 = 3 * gi + h, slot = t3 % kRing, ph = (t3 / kRing) & 1;
-                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), ph);                            // K-third landed
-                ptx::tc_fence_after();
-                if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 1 + h);
-                const uint64_t bs = bd0 + uint64_t((slot * kSlotBytes) >> 4);
-                static_assert(((2 * kTcLBO) >> 4) == 256, "B descriptor step of one K=16 MMA");
-                if (h < 2) ptx::umma_third_ts_w(d_tmem, a_tmem + 24 * h, bs, idesc, h == 0 ? 0u : 1u, ptx::smem_u32(&bars->empty[slot]));
-                else ptx::umma_third_last_w(d_tmem, a_tmem + 48, ad_aug, bs, idesc, ptx::smem_u32(&bars->empty[slot]), bar_accf);
+                const uint32_t t3 = 3 * gi + h;
+                slot[h] = t3 % kRing;
+                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot[h]]), (t3 / kRing) & 1);           // K-third landed
+              }
+              ptx::tc_fence_after();
+              if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 1);
+              static_assert(((2 * kTcLBO) >> 4) == 256, "B descriptor step of one K=16 MMA");
+              #pragma unroll
+              for (int h = 0; h < 3; ++h) {
+                const uint64_t bs = bd0 + uint64_t((slot[h] * kSlotBytes) >> 4);
+                if (h < 2) ptx::umma_third_ts_w(d_tmem, a_tmem + 24 * h, bs, idesc, h == 0 ? 0u : 1u, ptx::smem_u32(&bars->empty[slot[h]]));
+                else ptx::umma_third_last_w(d_tmem, a_tmem + 48, ad_aug, bs, idesc, ptx::smem_u32(&bars->empty[slot[h]]), bar_accf);
               }
               if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 4);
               if (c == 0) RVQ_TRACE(X, n, 1, lane == 0);
@@ -745,9 +752,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         const float thr = m + delta;
         uint32_t cm4[4] = {0u, 0u, 0u, 0u}, bm4[4] = {0u, 0u, 0u, 0u};
         #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          cm4[j & 3] |= (cm[j] <= thr) ? (1u << j) : 0u;
-          bm4[j & 3] |= (bmin[j] <= thr) ? (1u << j) : 0u;
+        for (int j = 0; j < 32; ++j) {                // two instructions per value: compare, predicated OR with an immediate
+          asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(cm4[j & 3]) : "f"(cm[j]), "f"(thr), "r"(1u << j));
+          asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bm4[j & 3]) : "f"(bmin[j]), "f"(thr), "r"(1u << j));
         }
         const uint32_t cmask = (cm4[0] | cm4[1]) | (cm4[2] | cm4[3]);
         const uint32_t bmask = ((bm4[0] | bm4[1]) | (bm4[2] | bm4[3])) >> (32 - 4 * nchunks);   // bit a = a-th batch processed
