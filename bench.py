@@ -30,8 +30,8 @@ UNIT = "frames/s"
 B, D, T, NQ, BINS, FRAME_RATE, BW = 64, 128, 750, 32, 1024, 75, 24.0
 FLOP_PER_FRAME_STAGE = 2 * BINS * D          # only the x.c^T contraction counts
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_encode_kernel launch at cfg2 (ncu --set full,
-# profiles/r1b_tc_encode_ncu_raw.csv): 51.04 MB + 1.60 MB; algorithmic: 24.6 MB latents + 12.3 MB codes (+ first touch of the pack)
-NCU_DRAM_BYTES_PER_LAUNCH = 52.64e6
+# profiles/r1c_tc_encode_ncu_raw.csv): 51.25 MB + 2.62 MB; algorithmic: 24.6 MB latents + 12.3 MB codes (+ first touch of the pack)
+NCU_DRAM_BYTES_PER_LAUNCH = 53.87e6
 WORKLOAD = f"cfg2: 24 kHz 24 kbps RVQ encode, latents [{B},{D},{T}] fp32, n_q={NQ}, bins={BINS}"
 
 
