@@ -75,21 +75,30 @@ struct Bars {
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
+// shared-window address of a barrier, from the CTA's window base (no generic->shared conversion inside the hot loops)
+#define RVQ_BAR(field, i) (sbase + Sm::bars + uint32_t(offsetof(Bars, field)) + 8u * uint32_t(i))
 static_assert(Sm::total <= 227 * 1024, "shared memory budget");
 static_assert(kTcKPad / 16 == 9 && kN == 128 && kTmemA + 2 * 64 == 512, "operand geometry");
 static_assert((Sm::m_size % 16) == 0 && (Sm::misc % 16) == 0, "alignment");
 
 // debug timeline of CTA 0 (slots 0/1, steps kTraceN0 .. kTraceN0 + kTraceSteps - 1): g_trace[X][step][event] = cycles since kernel start
-constexpr int kTraceSteps = 6, kTraceEv = 16, kTraceN0 = 2;
-__device__ long long g_trace[2 * kTraceSteps * kTraceEv + 128];   // + per-chunk detail of the MMA thread / the producer for (slot 0, step 4)
+#ifndef RVQ_TRACE_N0
+#define RVQ_TRACE_N0 2
+#endif
+constexpr int kTraceSteps = 6, kTraceEv = 16, kTraceN0 = RVQ_TRACE_N0;
+__device__ long long g_trace[2 * kTraceSteps * kTraceEv + 128 + 2 * 64];   // + per-chunk detail of the MMA thread / the producer for (slot 0, step 4)
 #ifdef RVQ_TC_TRACE
 #define RVQ_TRACE(X, n, ev, cond) do { if (blockIdx.x == 0 && (cond) && (n) >= kTraceN0 && (n) < kTraceN0 + kTraceSteps) { \
     asm volatile("" ::: "memory"); g_trace[(((X) * kTraceSteps) + (n) - kTraceN0) * kTraceEv + (ev)] = clock64() - t_kernel0; asm volatile("" ::: "memory"); } } while (0)
-#define RVQ_TRACE2(X, n, idx) do { if (blockIdx.x == 0 && (X) == 0 && (n) == 4) { \
+#define RVQ_TRACE2(X, n, idx) do { if (blockIdx.x == 0 && (X) == 0 && (n) == kTraceN0 + 2) { \
     asm volatile("" ::: "memory"); g_trace[2 * kTraceSteps * kTraceEv + (idx)] = clock64() - t_kernel0; asm volatile("" ::: "memory"); } } while (0)
+// update-pass detail (slot X, step 4): g_trace[base + 128 + 64 X + 8 u + e], lane 0 of update warp u
+#define RVQ_TRACE3(X, n, u, e) do { if (blockIdx.x == 0 && (n) == kTraceN0 + 2 && (threadIdx.x & 31) == 0) { \
+    asm volatile("" ::: "memory"); g_trace[2 * kTraceSteps * kTraceEv + 128 + 64 * (X) + 8 * (u) + (e)] = clock64() - t_kernel0; asm volatile("" ::: "memory"); } } while (0)
 #else
 #define RVQ_TRACE(X, n, ev, cond) do { } while (0)
 #define RVQ_TRACE2(X, n, idx) do { } while (0)
+#define RVQ_TRACE3(X, n, u, e) do { } while (0)
 #endif
 #ifdef RVQ_TC_TIMERS
 #define RVQ_TICK(acc) do { const unsigned tt_ = (unsigned)clock(); acc += tt_ - tc0; tc0 = tt_; } while (0)
@@ -134,6 +143,12 @@ __device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
   t[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
   const float a = ptx::fmin3(t[0], t[1], t[2]), b = ptx::fmin3(t[3], t[4], t[5]), c = ptx::fmin3(t[6], t[7], t[8]);
   return ptx::fmin3(ptx::fmin3(a, b, c), t[9], t[10]);
+}
+__device__ __forceinline__ float min16(const uint32_t (&v)[16]) {
+  float t[5];
+  #pragma unroll
+  for (int j = 0; j < 5; ++j) t[j] = ptx::fmin3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+  return fminf(ptx::fmin3(t[0], t[1], t[2]), ptx::fmin3(t[3], t[4], __uint_as_float(v[15])));
 }
 // squared rounding residue of two floats against their fp16 pair
 __device__ __forceinline__ float residue2(float a, float b, uint32_t& word, float e2) {
@@ -337,39 +352,84 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
 template <bool TRAIN>
 __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsigned char* ms, int u, int lane, int s, int rot,
                                             int nchunks, int64_t tile_n0, const float* __restrict__ t32,
-                                            const float* __restrict__ cn, uint32_t taddr, bool store, float& sq) {
+                                            const float* __restrict__ cn, uint32_t taddr, bool store, float& sq,
+                                            int trX, int trn, long long t_kernel0) {
   const int q = u & 3, h = u >> 2;
+  RVQ_TRACE3(trX, trn, u, 0);
   const int* qc = reinterpret_cast<const int*>(ms + Sm::m_qcnt);
   const int nslow = qc[0], nwide = qc[1];
   const int4* cand = reinterpret_cast<const int4*>(ms + Sm::m_cand);
+  const int* ncnt = reinterpret_cast<const int*>(ms + Sm::m_ncnt);
   const int g = lane >> 2, m = lane & 3;
   const int fA = q * 32 + h * 16 + g, fB = fA + 8;
+  // The winner rows of the certified frames are requested FIRST: they are in flight while the listed frames are resolved.
+  //   ncnt == 1: certified (or settled by an exact scan)   -> row requested now, subtracted below
+  //   ncnt 2..4: candidate list -> the resolving quarter-warp holds the winner's row and applies r <- r - q itself
+  //   ncnt kBig: wide set       -> only the code is resolved; the row is requested after the barrier
+  const int nA = ncnt[fA], nB = ncnt[fB];
+  float4 qa[8], qb[8];
+  {
+    const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
+    const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) qa[i] = nA == 1 ? __ldg(ra + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) qb[i] = nB == 1 ? __ldg(rb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (nslow + nwide > 0) {
-    const int qq = lane >> 3, j = lane & 7;
     const unsigned char* slowq = ms + Sm::m_slowq;
     const unsigned char* wideq = ms + Sm::m_wideq;
-    // candidate lists: item qi goes to quarter qi / 8 of warp qi % 8 (the first eight items land on eight different
-    // warps), then qi + 32, ...; a warp none of whose quarters has an item skips the body
+    // candidate lists (2..4 codes): one frame per warp at a time, lane = 16-byte chunk of the row, so a frame costs a
+    // handful of registers next to the rows in flight above.  Exact fp32 distances (core_vq.py:183-187), lowest code on
+    // ties; the warp holds the winner's row and applies r <- r - q right here.
     #pragma unroll 1
-    for (int qi = qq * kUpdWarps + u; qi < ((nslow + 31) & ~31); qi += 32) {
-      const int f = qi < nslow ? int(slowq[qi]) : -1;
-      if (!__any_sync(0xffffffffu, f >= 0)) continue;
+    for (int i = u; i < nslow; i += kUpdWarps) {
+      const int f = slowq[i];
+      // the 2..4 candidates = flagged batches x flagged classes (warp-uniform enumeration; bit a of the batch mask is the
+      // a-th batch in this CTA's processing order)
       int4 cd = make_int4(-1, -1, -1, -1);
-      if (f >= 0) cd = cand[f];
-      Cand<4> k;
-      k.c[0] = cd.x; k.c[1] = cd.y; k.c[2] = cd.z; k.c[3] = cd.w;
-      load_cand<4>(k, j, t32, cn);
-      Row4 r;
+      {
+        const uint32_t cmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
+        uint32_t bm2 = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + f * 4);
+        int w = 0;
+        while (bm2) {
+          const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
+          int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
+          const int base = pc * 128 + (a & 3) * 32;
+          uint32_t cm2 = cmk;
+          while (cm2) {
+            const int code = base + __ffs(cm2) - 1; cm2 &= cm2 - 1;
+            if (w == 0) cd.x = code; else if (w == 1) cd.y = code; else if (w == 2) cd.z = code; else cd.w = code;
+            ++w;
+          }
+        }
+      }
+      float* rp = rs + rs_off(f, lane);
+      const float4 rl = *reinterpret_cast<const float4*>(rp);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.x) * 128) + lane);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.y) * 128) + lane);
+      const float4 w2 = cd.z >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.z) * 128) + lane) : z4;
+      const float4 w3 = cd.w >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.w) * 128) + lane) : z4;
+      const float n0 = __ldg(cn + cd.x), n1 = __ldg(cn + cd.y);
+      const float n2 = cd.z >= 0 ? __ldg(cn + cd.z) : 0.f, n3 = cd.w >= 0 ? __ldg(cn + cd.w) : 0.f;
+      float rr = dot4(rl, rl, 0.f), d0 = dot4(rl, w0, 0.f), d1 = dot4(rl, w1, 0.f), d2 = dot4(rl, w2, 0.f), d3 = dot4(rl, w3, 0.f);
       #pragma unroll
-      for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f >= 0) r = load_res(rs, f, j);
-      const float rr = quarter_sum(dot_row(r, r));
-      // core_vq.py:183-187, lowest index on ties; NaN distances: keep the first candidate unless a finite one exists
-      float best = inf_f(); int bcode = 0x7fffffff, bidx = 0;
-      score_cand<4>(k, r, rr, best, bcode, bidx);
+      for (int off = 16; off > 0; off >>= 1) {
+        rr += __shfl_xor_sync(0xffffffffu, rr, off);
+        d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
+      }
+      float best = inf_f(); int bcode = 0x7fffffff; float4 wsel = w0;     // NaN distances only: the first candidate
+      auto consider = [&](float d, float nrm, int code, const float4& w) {
+        const float e = (rr - 2.f * d) + nrm;
+        if (code >= 0 && (e < best || (e == best && code < bcode))) { best = e; bcode = code; wsel = w; }
+      };
+      consider(d0, n0, cd.x, w0); consider(d1, n1, cd.y, w1); consider(d2, n2, cd.z, w2); consider(d3, n3, cd.w, w3);
       if (bcode == 0x7fffffff) bcode = cd.x;
+      *reinterpret_cast<float4*>(rp) = sub_row<TRAIN>(p, rl, wsel);
       const int64_t nfr = tile_n0 + f;
-      if (f >= 0 && j == 0) {
+      if (lane == 0) {
         *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;
         if (f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
       }
@@ -377,21 +437,27 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     // wide candidate sets: one frame per warp at a time, handed out from the last warp down
     #pragma unroll 1
     for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
+    RVQ_TRACE3(trX, trn, u, 1);
+    ptx::named_bar_sync(6, kUpdWarps * 32);      // listed frames are updated, wide frames have their winner
+    RVQ_TRACE3(trX, trn, u, 2);
+    if (nwide > 0 && __any_sync(0xffffffffu, nA == kBig || nB == kBig)) {
+      const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
+      const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
+      if (nA == kBig) {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) qa[i] = __ldg(ra + 4 * i);
+      }
+      if (nB == kBig) {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
+      }
+    }
   }
-  if (nslow + nwide > 0) ptx::named_bar_sync(6, kUpdWarps * 32);      // every listed / wide frame of the tile has its winner
-  // both winner rows in flight
-  float4 qa[8], qb[8];
-  {
-    const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
-    const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
-    #pragma unroll
-    for (int i = 0; i < 8; ++i) qa[i] = __ldg(ra + 4 * i);
-    #pragma unroll
-    for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
-  }
+  const bool doneA = nA >= 2 && nA <= 4, doneB = nB >= 2 && nB <= 4;     // already updated by the resolving quarter-warp
+  RVQ_TRACE3(trX, trn, u, 3);
   uint32_t w[32];
   float e2a, e2b;
-  auto process = [&](int f, const float4 (&qr)[8], int half, float& e2) {
+  auto process = [&](int f, const float4 (&qr)[8], int half, float& e2, bool done) {
     const int sw = rs_swz(f);
     float* rbase = rs + f * 128 + ((m ^ (sw & 3)) << 2);
     float e[4] = {0.f, 0.f, 0.f, 0.f};
@@ -399,7 +465,8 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4* rp = reinterpret_cast<float4*>(rbase + ((i ^ (sw >> 2)) << 4));
-      const float4 n = sub_row<TRAIN>(p, *rp, qr[i]);
+      const float4 rv = *rp;
+      const float4 n = done ? rv : sub_row<TRAIN>(p, rv, qr[i]);
       *rp = n;
       e[i & 3] = residue2(n.x, n.y, w[4 * i + 2 * half], e[i & 3]);
       e[i & 3] = residue2(n.z, n.w, w[4 * i + 2 * half + 1], e[i & 3]);
@@ -408,8 +475,10 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     e2 = (e[0] + e[1]) + (e[2] + e[3]);
     if (TRAIN && f < p.tf && tile_n0 + f < p.N) sq += sqf;      // sum((q - r)^2) of core_vq.py:319 = |new residual|^2
   };
-  process(fA, qa, 0, e2a);
-  process(fB, qb, 1, e2b);
+  process(fA, qa, 0, e2a, doneA);
+  RVQ_TRACE3(trX, trn, u, 4);
+  process(fB, qb, 1, e2b, doneB);
+  RVQ_TRACE3(trX, trn, u, 5);
   // exact rounding residue of the new operand rows: sum over the 4 lanes of the group
   e2a += __shfl_xor_sync(0xffffffffu, e2a, 1); e2b += __shfl_xor_sync(0xffffffffu, e2b, 1);
   e2a += __shfl_xor_sync(0xffffffffu, e2a, 2); e2b += __shfl_xor_sync(0xffffffffu, e2b, 2);
@@ -419,6 +488,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     dr2[fB] = e2b; dr2[kM + fB] = 0.f;
   }
   if (store) ptx::tmem_st_16x256b_x8(taddr, w);
+  RVQ_TRACE3(trX, trn, u, 6);
 }
 
 }  // namespace
@@ -442,9 +512,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   const int steps0 = ((tcnt + 1) >> 1) * p.n_q, steps1 = (tcnt >> 1) * p.n_q;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRing; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1); }
-    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->a_ready[i]), kUpdWarps); ptx::mbar_init(ptx::smem_u32(&bars->cand_ready[i]), 4); }
+    for (int i = 0; i < kRing; ++i) { ptx::mbar_init(RVQ_BAR(full, i), 1); ptx::mbar_init(RVQ_BAR(empty, i), 1); }
+    for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(RVQ_BAR(acc_full, i), 1); ptx::mbar_init(RVQ_BAR(acc_empty, i), 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(RVQ_BAR(a_ready, i), kUpdWarps); ptx::mbar_init(RVQ_BAR(cand_ready, i), 4); }
     ptx::fence_mbar_init();
   }
   if (threadIdx.x < 2) {
@@ -486,9 +556,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
               const int pc = c + rot < nchunks ? c + rot : c + rot - nchunks;
               #pragma unroll 1
               for (int third = 0; third < 3; ++third) {
-                ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), ph ^ 1);
+                ptx::mbar_wait(RVQ_BAR(empty, slot), ph ^ 1);
                 ptx::bulk_g2s_expect_w(sbase + Sm::ring + slot * kSlotBytes, img + size_t(pc) * kTcChunkBytes + third * kSlotBytes,
-                                       kSlotBytes, ptx::smem_u32(&bars->full[slot]));
+                                       kSlotBytes, RVQ_BAR(full, slot));
                 if (++slot == kRing) { slot = 0; ph ^= 1; }
               }
             }
@@ -510,12 +580,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         const uint64_t bd0 = ptx::umma_desc_kmajor_noswz(sbase + Sm::ring, kTcLBO, kTcSBO);
         const uint32_t who = uint32_t(warp - 13);
         const uint32_t d_tmem = tmem_u + who * kN;
-        const uint32_t bar_accf = ptx::smem_u32(&bars->acc_full[who]), bar_acce = ptx::smem_u32(&bars->acc_empty[who]);
+        const uint32_t bar_accf = RVQ_BAR(acc_full, who), bar_acce = RVQ_BAR(acc_empty, who);
         uint32_t gi = 0, bph = 0;              // global chunk index, phase of this issuer's accumulator buffer
         for (int n = 0; n < steps0; ++n) {
           for (int X = 0; X < 2; ++X) {
             if (X == 1 && n >= steps1) break;
-            ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[X]), uint32_t(n) & 1);       // fp16 operand of this step is in TMEM
+            ptx::mbar_wait(RVQ_BAR(a_ready, X), uint32_t(n) & 1);       // fp16 operand of this step is in TMEM
             ptx::tc_fence_after();
             RVQ_TRACE(X, n, 0, who == 0 && lane == 0);
             const uint32_t a_tmem = tmem_u + kTmemA + 64 * X;
@@ -531,7 +601,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
               for (int h = 0; h < 3; ++h) {
                 const uint32_t t3 = 3 * gi + h;
                 slot[h] = t3 % kRing;
-                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot[h]]), (t3 / kRing) & 1);           // K-third landed
+                ptx::mbar_wait(RVQ_BAR(full, slot[h]), (t3 / kRing) & 1);           // K-third landed
               }
               ptx::tc_fence_after();
               if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 1);
@@ -539,8 +609,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
               #pragma unroll
               for (int h = 0; h < 3; ++h) {
                 const uint64_t bs = bd0 + uint64_t((slot[h] * kSlotBytes) >> 4);
-                if (h < 2) ptx::umma_third_ts_w(d_tmem, a_tmem + 24 * h, bs, idesc, h == 0 ? 0u : 1u, ptx::smem_u32(&bars->empty[slot[h]]));
-                else ptx::umma_third_last_w(d_tmem, a_tmem + 48, ad_aug, bs, idesc, ptx::smem_u32(&bars->empty[slot[h]]), bar_accf);
+                if (h < 2) ptx::umma_third_ts_w(d_tmem, a_tmem + 24 * h, bs, idesc, h == 0 ? 0u : 1u, RVQ_BAR(empty, slot[h]));
+                else ptx::umma_third_last_w(d_tmem, a_tmem + 48, ad_aug, bs, idesc, RVQ_BAR(empty, slot[h]), bar_accf);
               }
               if (lane == 0) RVQ_TRACE2(X, n, 8 * c + 4);
               if (c == 0) RVQ_TRACE(X, n, 1, lane == 0);
@@ -599,7 +669,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[X]));
+      if (lane == 0) ptx::mbar_arrive(RVQ_BAR(a_ready, X));
     };
     // n = -1 is the prologue: it only loads the first tile of each slot (one call site for the tile load)
     for (int n = -1; n < steps0; ++n) {
@@ -616,7 +686,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           unsigned char* ms = smem + Sm::misc + X * Sm::m_size;
           // winners / candidate lists of this step: one warp polls the mbarrier, the others block on a hardware barrier
           // (a blocked warp costs no issue slots, a polling one does)
-          if (u == 0) ptx::mbar_wait(ptx::smem_u32(&bars->cand_ready[X]), uint32_t(n) & 1);
+          if (u == 0) ptx::mbar_wait(RVQ_BAR(cand_ready, X), uint32_t(n) & 1);
           ptx::named_bar_sync(8, kUpdWarps * 32);
           RVQ_TICK(t_wait);
           RVQ_TRACE(X, n, 6, u == 0 && lane == 0);
@@ -624,7 +694,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           float sq = 0.f;
           // operand rows of this warp: TMEM lanes 32q + 16h .. +15, columns of slot X
           update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st),
-                             tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, sq);
+                             tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, sq, X, n,
+#ifdef RVQ_TC_TRACE
+                             t_kernel0
+#else
+                             0
+#endif
+                             );
           RVQ_TICK(t_upd);
           RVQ_TRACE(X, n, 7, u == 0 && lane == 0);
           if (threadIdx.x == 128) { int* qc = reinterpret_cast<int*>(ms + Sm::m_qcnt); qc[0] = 0; qc[1] = 0; }
@@ -632,7 +708,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[X]));
+            if (lane == 0) ptx::mbar_arrive(RVQ_BAR(a_ready, X));
             RVQ_TICK(t_stw);
             RVQ_TRACE(X, n, 8, u == 0 && lane == 0);
           } else {
@@ -689,6 +765,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         const float* t32 = pv.tab32(st);
         const float* cn = pv.cnorm(st);
         const StageMeta* meta = pv.meta(st);
+        // margin coefficients of this stage: requested before the chunk loop, used after it
+        const float mt_coef = __ldg(&meta->margin_coef), mt_abs = __ldg(&meta->margin_abs), mt_xlimit = __ldg(&meta->xlimit);
+        const float mt_cmax = __ldg(&meta->cmax_all), mt_dr = __ldg(&meta->margin_dr);
         RVQ_TICK0();
         // ---- scores: per-class and per-batch minima of the K approximate scores of this frame ----
         float cm[32], bmin[32];
@@ -696,37 +775,62 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         for (int j = 0; j < 32; ++j) { cm[j] = inf_f(); bmin[j] = inf_f(); }
         // one rolled iteration per 128-code chunk (the hot loops of a stage must stay inside the instruction cache);
         // bmin is a shift register: after the loop the a-th batch in processing order sits at 32 - 4*nchunks + a
+        // The 128 columns of a chunk are read as four groups of 2 x 16 columns, G0 = {0-15, 32-47}, G1 = {16-31, 48-63},
+        // G2 = {64-79, 96-111}, G3 = {80-95, 112-127} (16 classes of two batches each), into two register sets: while one
+        // set is reduced the other one's tcgen05.ld is in flight, across chunk boundaries too.
+        uint32_t pa[16], pb[16], qa[16], qb[16];
+        auto ld_group = [&](uint32_t buf, int g, uint32_t (&x0)[16], uint32_t (&x1)[16]) {
+          const uint32_t col = tlane + buf * kN + (g >> 1) * 64 + (g & 1) * 16;
+          ptx::tmem_ld16(col, x0);
+          ptx::tmem_ld16(col + 32, x1);
+        };
+        // class minima of the group's 16 classes (offset o) and the two partial batch minima (h0: first batch, h1: second)
+        auto reduce_group = [&](const uint32_t (&x0)[16], const uint32_t (&x1)[16], int o, float& h0, float& h1) {
+          #pragma unroll
+          for (int j = 0; j < 16; ++j) cm[o + j] = ptx::fmin3(cm[o + j], __uint_as_float(x0[j]), __uint_as_float(x1[j]));
+          h0 = min16(x0);
+          h1 = min16(x1);
+        };
+        uint32_t buf = acc_it % kAccBufs;
+        ptx::mbar_wait(RVQ_BAR(acc_full, buf), (acc_it / kAccBufs) & 1);
+        ptx::tc_fence_after();
+        ++acc_it;
+        RVQ_TICK(t_wait);
+        RVQ_TRACE(X, n, 3, warp == 0 && lane == 0);
+        ld_group(buf, 0, pa, pb);
+        ld_group(buf, 1, qa, qb);
         #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
-          const uint32_t buf = acc_it % kAccBufs, aph = (acc_it / kAccBufs) & 1;
-          ++acc_it;
-          ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), aph);
-          ptx::tc_fence_after();
-          RVQ_TICK(t_wait);
-          if (c == 0) RVQ_TRACE(X, n, 3, warp == 0 && lane == 0);
           if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c);
-          uint32_t v0[32], v1[32];
-          ptx::tmem_ld32(tlane + buf * kN, v0);
-          ptx::tmem_ld32(tlane + buf * kN + 32, v1);
+          float h0, h1, g0, g1;
           #pragma unroll
           for (int j = 0; j < 28; ++j) bmin[j] = bmin[j + 4];
-          ptx::tmem_ld_wait();
-          #pragma unroll
-          for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
-          bmin[28] = min32(v0);
-          bmin[29] = min32(v1);
-          ptx::tmem_ld32(tlane + buf * kN + 64, v0);
-          ptx::tmem_ld32(tlane + buf * kN + 96, v1);
-          ptx::tmem_ld_wait();
-          // scores are in registers: hand the accumulator back before reducing them
+          ptx::tmem_ld_wait();                                   // G0, G1
+          reduce_group(pa, pb, 0, h0, h1);
+          ld_group(buf, 2, pa, pb);
+          reduce_group(qa, qb, 16, g0, g1);
+          bmin[28] = fminf(h0, g0);
+          bmin[29] = fminf(h1, g1);
+          ptx::tmem_ld_wait();                                   // G2
+          ld_group(buf, 3, qa, qb);
+          reduce_group(pa, pb, 0, h0, h1);
+          ptx::tmem_ld_wait();                                   // G3: the whole chunk is in registers, hand the accumulator back
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));
+          if (lane == 0) ptx::mbar_arrive(RVQ_BAR(acc_empty, buf));
           if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c + 1);
-          #pragma unroll
-          for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
-          bmin[30] = min32(v0);
-          bmin[31] = min32(v1);
+          const bool more = c + 1 < nchunks;
+          if (more) {                                            // next chunk's G0 flies while G3 is reduced
+            buf = acc_it % kAccBufs;
+            ptx::mbar_wait(RVQ_BAR(acc_full, buf), (acc_it / kAccBufs) & 1);
+            ptx::tc_fence_after();
+            ++acc_it;
+            ld_group(buf, 0, pa, pb);
+          }
+          reduce_group(qa, qb, 16, g0, g1);
+          if (more) ld_group(buf, 1, qa, qb);
+          bmin[30] = fminf(h0, g0);
+          bmin[31] = fminf(h1, g1);
           RVQ_TICK(t_epi);
           if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c + 2);
         }
@@ -736,9 +840,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         float xx = X ? xx_1 : xx_0;
         if (s == 0) xx = reinterpret_cast<const float*>(ms + Sm::m_cmask)[f] + reinterpret_cast<const float*>(ms + Sm::m_bmask)[f];
         const float xnorm = sqrtf(xx);
-        const bool outl = !(xnorm < meta->xlimit);      // also true for NaN
+        const bool outl = !(xnorm < mt_xlimit);      // also true for NaN
         const float drn = sqrtf(reinterpret_cast<const float*>(ms + Sm::m_dr2)[f] + reinterpret_cast<const float*>(ms + Sm::m_dr2)[kM + f]) * 1.001f;
-        const float delta = meta->margin_coef * xnorm + meta->margin_dr * drn + meta->margin_abs;
+        const float delta = mt_coef * xnorm + mt_dr * drn + mt_abs;
         // ---- candidates: certified winner / up to 4 codes to re-score / mask enumeration / exact scan ----
         float m4[4];
         #pragma unroll
@@ -763,23 +867,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         const int ncand = nc * nb;
         // bmask bit a = a-th batch in this CTA's processing order; its codes start at batch_base(a)
         auto batch_base = [&](int a) { int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks; return pc * 128 + (a & 3) * 32; };
-        int4 cd = make_int4(batch_base(__ffs(bmask) - 1) + (__ffs(cmask) - 1), -1, -1, -1);
-        if (!full && ncand > 1 && ncand <= 4) {
-          int cc[4] = {-1, -1, -1, -1};
-          int w = 0;
-          uint32_t bm2 = bmask;
-          while (bm2) {
-            const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
-            uint32_t cm2 = cmask;
-            while (cm2) {
-              const int j = __ffs(cm2) - 1; cm2 &= cm2 - 1;
-              const int code = batch_base(a) + j;
-              if (w == 0) cc[0] = code; else if (w == 1) cc[1] = code; else if (w == 2) cc[2] = code; else cc[3] = code;
-              ++w;
-            }
-          }
-          cd = make_int4(cc[0], cc[1], cc[2], cc[3]);
-        }
+        // first candidate (= the winner when certified); the update warps enumerate the other codes of a short list
+        // from the two masks
+        const int4 cd = make_int4(batch_base(__ffs(bmask) - 1) + (__ffs(cmask) - 1), -1, -1, -1);
         *reinterpret_cast<int4*>(ms + Sm::m_cand + f * 16) = cd;
         *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
         *reinterpret_cast<uint32_t*>(ms + Sm::m_cmask + f * 4) = cmask;
@@ -803,11 +893,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         n_full += full ? 1u : 0u; n_cert += (!full && ncand == 1) ? 1u : 0u; n_resc += (!full && ncand > 1) ? 1u : 0u;
         // upper bound of the next residual's |r|^2 (only the margin and the validity test use it):
         // the winner's approximate score is <= m + delta and off by <= delta/2
-        if (full) { const float g2 = xnorm + meta->cmax_all; xx = g2 * g2; }
+        if (full) { const float g2 = xnorm + mt_cmax; xx = g2 * g2; }
         else xx = fmaxf(xx + m + 1.5f * delta, 0.f) * 1.00001f + 1e-30f;
         if (X) xx_1 = xx; else xx_0 = xx;
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->cand_ready[X]));    // winners and queues visible to the update warps
+        if (lane == 0) ptx::mbar_arrive(RVQ_BAR(cand_ready, X));    // winners and queues visible to the update warps
         RVQ_TRACE(X, n, 5, warp == 0 && lane == 0);
         RVQ_TICK(t_win);
       }
@@ -839,7 +929,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
 }
 
 int tc_debug_trace(long long* out_host, int n) {
-  const int m = n < 2 * kTraceSteps * kTraceEv + 128 ? n : 2 * kTraceSteps * kTraceEv + 128;
+  const int cap = 2 * kTraceSteps * kTraceEv + 128 + 2 * 64;
+  const int m = n < cap ? n : cap;
   RVQ_CUDA(cudaMemcpyFromSymbol(out_host, g_trace, size_t(m) * sizeof(long long)));
   return m;
 }

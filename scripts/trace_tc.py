@@ -15,7 +15,8 @@ for _ in range(3): ops.encode(pk, x, 0, 32)
 torch.cuda.synchronize()
 lib = L.load()
 STEPS, EV = 6, 16
-arr = (C.c_longlong * (2 * STEPS * EV + 128))()
+N0 = int(os.environ.get('TRACE_N0', 2))   # must match -DRVQ_TRACE_N0 of the build
+arr = (C.c_longlong * (2 * STEPS * EV + 128 + 128))()
 lib.rvq_debug_trace.restype = C.c_int
 lib.rvq_debug_trace.argtypes = [C.c_void_p, C.c_int]
 lib.rvq_debug_trace(arr, len(arr))
@@ -24,11 +25,15 @@ names = ["mma:A seen", "mma:chunk0 issued", "mma:all issued", "score:first acc",
 for n in range(STEPS):
     for X in range(2):
         ev = [arr[(X * STEPS + n) * EV + e] for e in range(9)]
-        print(f"step {n + 2} slot {X}: " + "  ".join(f"{nm}={v}" for nm, v in zip(names, ev)))
+        print(f"step {n + N0} slot {X}: " + "  ".join(f"{nm}={v}" for nm, v in zip(names, ev)))
 base = 2 * STEPS * EV
-print("MMA thread, slot 0 step 4, per chunk: acc free | third0 landed | third1 | third2 | all issued")
+print("MMA thread, slot 0 step N0+2, per chunk: acc free | third0 landed | third1 | third2 | all issued")
 for c in range(8):
     print(f"  chunk {c}: " + "  ".join(str(arr[base + 8 * c + e]) for e in range(5)))
-print("update warps, slot 0 step 4: start | lists done | wide done | barrier | rows requested | frame A done | frame B done | operand stored")
-for u in range(8):
-    print(f"  warp {u}: " + "  ".join(str(arr[base + 64 + 8 * u + e]) for e in range(8)))
+print("score warp 0, slot 0 step N0+2, per chunk: acc_full seen | accumulator released | minima done")
+for c in range(8):
+    print(f"  chunk {c}: " + "  ".join(str(arr[base + 64 + 3 * c + e]) for e in range(3)))
+for X in range(2):
+    print(f"update warps, slot {X} step N0+2: start | resolve done | barrier passed | rows requested | frame A done | frame B done | operand stored")
+    for u in range(8):
+        print(f"  warp {u}: " + "  ".join(str(arr[base + 128 + 64 * X + 8 * u + e]) for e in range(7)))
