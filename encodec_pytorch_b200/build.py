@@ -36,7 +36,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     defs = [f"-D{d}" for d in os.environ.get("RVQ_NVCC_DEFS", "").split() if d]   # e.g. RVQ_TC_TRACE RVQ_TC_TIMERS
-    cmd = [nvcc, *NVCC_FLAGS, *defs, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    if os.environ.get("RVQ_TC_SRC"):                       # A/B runs: another revision of the tcgen05 kernel file
+        srcs[-1] = os.path.join(CSRC, os.environ["RVQ_TC_SRC"])
+    cmd = [nvcc, *NVCC_FLAGS, *defs, "-o", LIB, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -71,7 +71,7 @@ struct Sm {
   static constexpr uint32_t total = bars + 256;
 };
 struct Bars {
-  uint64_t full[kRing], empty[kRing], acc_full[kAccBufs], acc_empty[kAccBufs], a_ready[2], cand_ready[2];
+  uint64_t full[kRing], empty[kRing], acc_full[kAccBufs], acc_empty[kAccBufs], a_ready[2], cand_ready[2], dr_ready[2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
@@ -144,17 +144,23 @@ __device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
   const float a = ptx::fmin3(t[0], t[1], t[2]), b = ptx::fmin3(t[3], t[4], t[5]), c = ptx::fmin3(t[6], t[7], t[8]);
   return ptx::fmin3(ptx::fmin3(a, b, c), t[9], t[10]);
 }
-__device__ __forceinline__ float min16(const uint32_t (&v)[16]) {
-  float t[5];
-  #pragma unroll
-  for (int j = 0; j < 5; ++j) t[j] = ptx::fmin3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
-  return fminf(ptx::fmin3(t[0], t[1], t[2]), ptx::fmin3(t[3], t[4], __uint_as_float(v[15])));
+// code of (batch a in this CTA's processing order, class j): batch = 32 consecutive codes, class = code mod 32
+__device__ __forceinline__ int code_of(int a, int j, int rot, int nchunks) {
+  int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
+  return pc * 128 + (a & 3) * 32 + j;
 }
 // squared rounding residue of two floats against their fp16 pair
 __device__ __forceinline__ float residue2(float a, float b, uint32_t& word, float e2) {
   const __half2 h = __floats2half2_rn(a, b);
   word = *reinterpret_cast<const uint32_t*>(&h);
   const float2 bk = __half22float2(h);
+  const float ea = a - bk.x, eb = b - bk.y;
+  return fmaf(eb, eb, fmaf(ea, ea, e2));
+}
+
+// squared rounding residue of two floats against their (already packed) fp16 pair
+__device__ __forceinline__ float residue_of(float a, float b, uint32_t word, float e2) {
+  const float2 bk = __half22float2(*reinterpret_cast<const __half2*>(&word));
   const float ea = a - bk.x, eb = b - bk.y;
   return fmaf(eb, eb, fmaf(ea, ea, e2));
 }
@@ -301,8 +307,6 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
     const int a = bmq ? __ffs(bmq) - 1 : -1;
     #pragma unroll
     for (int i = 0; i < 4; ++i) bmq &= bmq - 1;
-    int base = 0;
-    if (a >= 0) { int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks; base = pc * 128 + (a & 3) * 32; }   // processing order -> code
     uint32_t cmq = cm;
     #pragma unroll 1
     for (int oc = 0; oc < nc; oc += 2) {
@@ -311,7 +315,7 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
       for (int u = 0; u < 2; ++u) {
         const int jj = cmq ? __ffs(cmq) - 1 : -1;
         cmq &= cmq - 1;
-        k.c[u] = (a >= 0 && jj >= 0) ? base + jj : -1;
+        k.c[u] = (a >= 0 && jj >= 0) ? code_of(a, jj, rot, nchunks) : -1;
       }
       load_cand<2>(k, j, t32, cn);
       score_cand<2>(k, r, rr, best, bcode, bidx);
@@ -328,8 +332,7 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
   bool mine = bcode == wc;
   if (wc == 0x7fffffff) {                                  // NaN distances only: lowest candidate, like an exact scan would
     mine = qq == 0;
-    if (mine) { const int c0 = (__ffs(bm) - 1); int pc = (c0 >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
-                bcode = pc * 128 + (c0 & 3) * 32 + (__ffs(cm) - 1); }
+    if (mine) bcode = code_of(__ffs(bm) - 1, __ffs(cm) - 1, rot, nchunks);
   }
   const int64_t nfr = tile_n0 + f;
   if (mine && j == 0) {
@@ -352,7 +355,7 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
 template <bool TRAIN>
 __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsigned char* ms, int u, int lane, int s, int rot,
                                             int nchunks, int64_t tile_n0, const float* __restrict__ t32,
-                                            const float* __restrict__ cn, uint32_t taddr, bool store, float& sq,
+                                            const float* __restrict__ cn, uint32_t taddr, bool store, uint32_t bar_a, float& sq,
                                             int trX, int trn, long long t_kernel0) {
   const int q = u & 3, h = u >> 2;
   RVQ_TRACE3(trX, trn, u, 0);
@@ -367,6 +370,64 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   //   ncnt 2..4: candidate list -> the resolving quarter-warp holds the winner's row and applies r <- r - q itself
   //   ncnt kBig: wide set       -> only the code is resolved; the row is requested after the barrier
   const int nA = ncnt[fA], nB = ncnt[fB];
+  const unsigned char* slowq = ms + Sm::m_slowq;
+  const unsigned char* wideq = ms + Sm::m_wideq;
+  // candidate lists (2..4 codes): one frame per warp at a time, lane = 16-byte chunk of the row, so a frame costs a
+  // handful of registers next to the winner rows in flight.  Exact fp32 distances (core_vq.py:183-187), lowest code on
+  // ties; the warp holds the winner's row and applies r <- r - q itself.
+  struct Item { int f; int4 cd; float* rp; float4 rl, w0, w1, w2, w3; float n0, n1, n2, n3; };
+  auto item_load = [&](int i, Item& it) {
+    it.f = slowq[i];
+    // the 2..4 candidates = flagged batches x flagged classes (warp-uniform enumeration; bit a of the batch mask is the
+    // a-th batch in this CTA's processing order)
+    it.cd = make_int4(-1, -1, -1, -1);
+    const uint32_t cmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + it.f * 4);
+    uint32_t bm2 = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + it.f * 4);
+    int w = 0;
+    while (bm2) {
+      const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
+      uint32_t cm2 = cmk;
+      while (cm2) {
+        const int code = code_of(a, __ffs(cm2) - 1, rot, nchunks); cm2 &= cm2 - 1;
+        if (w == 0) it.cd.x = code; else if (w == 1) it.cd.y = code; else if (w == 2) it.cd.z = code; else it.cd.w = code;
+        ++w;
+      }
+    }
+    it.rp = rs + rs_off(it.f, lane);
+    it.rl = *reinterpret_cast<const float4*>(it.rp);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    it.w0 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.x) * 128) + lane);
+    it.w1 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.y) * 128) + lane);
+    it.w2 = it.cd.z >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.z) * 128) + lane) : z4;
+    it.w3 = it.cd.w >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.w) * 128) + lane) : z4;
+    it.n0 = __ldg(cn + it.cd.x); it.n1 = __ldg(cn + it.cd.y);
+    it.n2 = it.cd.z >= 0 ? __ldg(cn + it.cd.z) : 0.f; it.n3 = it.cd.w >= 0 ? __ldg(cn + it.cd.w) : 0.f;
+  };
+  auto item_finish = [&](const Item& it) {
+    float rr = dot4(it.rl, it.rl, 0.f), d0 = dot4(it.rl, it.w0, 0.f), d1 = dot4(it.rl, it.w1, 0.f), d2 = dot4(it.rl, it.w2, 0.f),
+          d3 = dot4(it.rl, it.w3, 0.f);
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      rr += __shfl_xor_sync(0xffffffffu, rr, off);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
+    }
+    float best = inf_f(); int bcode = 0x7fffffff; float4 wsel = it.w0;     // NaN distances only: the first candidate
+    auto consider = [&](float d, float nrm, int code, const float4& w) {
+      const float e = (rr - 2.f * d) + nrm;
+      if (code >= 0 && (e < best || (e == best && code < bcode))) { best = e; bcode = code; wsel = w; }
+    };
+    consider(d0, it.n0, it.cd.x, it.w0); consider(d1, it.n1, it.cd.y, it.w1);
+    consider(d2, it.n2, it.cd.z, it.w2); consider(d3, it.n3, it.cd.w, it.w3);
+    if (bcode == 0x7fffffff) bcode = it.cd.x;
+    *reinterpret_cast<float4*>(it.rp) = sub_row<TRAIN>(p, it.rl, wsel);
+    const int64_t nfr = tile_n0 + it.f;
+    if (lane == 0) {
+      *reinterpret_cast<int*>(ms + Sm::m_cand + it.f * 16) = bcode;
+      if (it.f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
+    }
+  };
+  Item it;
   float4 qa[8], qb[8];
   {
     const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
@@ -377,63 +438,8 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     for (int i = 0; i < 8; ++i) qb[i] = nB == 1 ? __ldg(rb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (nslow + nwide > 0) {
-    const unsigned char* slowq = ms + Sm::m_slowq;
-    const unsigned char* wideq = ms + Sm::m_wideq;
-    // candidate lists (2..4 codes): one frame per warp at a time, lane = 16-byte chunk of the row, so a frame costs a
-    // handful of registers next to the rows in flight above.  Exact fp32 distances (core_vq.py:183-187), lowest code on
-    // ties; the warp holds the winner's row and applies r <- r - q right here.
     #pragma unroll 1
-    for (int i = u; i < nslow; i += kUpdWarps) {
-      const int f = slowq[i];
-      // the 2..4 candidates = flagged batches x flagged classes (warp-uniform enumeration; bit a of the batch mask is the
-      // a-th batch in this CTA's processing order)
-      int4 cd = make_int4(-1, -1, -1, -1);
-      {
-        const uint32_t cmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
-        uint32_t bm2 = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + f * 4);
-        int w = 0;
-        while (bm2) {
-          const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
-          int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks;
-          const int base = pc * 128 + (a & 3) * 32;
-          uint32_t cm2 = cmk;
-          while (cm2) {
-            const int code = base + __ffs(cm2) - 1; cm2 &= cm2 - 1;
-            if (w == 0) cd.x = code; else if (w == 1) cd.y = code; else if (w == 2) cd.z = code; else cd.w = code;
-            ++w;
-          }
-        }
-      }
-      float* rp = rs + rs_off(f, lane);
-      const float4 rl = *reinterpret_cast<const float4*>(rp);
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.x) * 128) + lane);
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.y) * 128) + lane);
-      const float4 w2 = cd.z >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.z) * 128) + lane) : z4;
-      const float4 w3 = cd.w >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(cd.w) * 128) + lane) : z4;
-      const float n0 = __ldg(cn + cd.x), n1 = __ldg(cn + cd.y);
-      const float n2 = cd.z >= 0 ? __ldg(cn + cd.z) : 0.f, n3 = cd.w >= 0 ? __ldg(cn + cd.w) : 0.f;
-      float rr = dot4(rl, rl, 0.f), d0 = dot4(rl, w0, 0.f), d1 = dot4(rl, w1, 0.f), d2 = dot4(rl, w2, 0.f), d3 = dot4(rl, w3, 0.f);
-      #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        rr += __shfl_xor_sync(0xffffffffu, rr, off);
-        d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
-        d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
-      }
-      float best = inf_f(); int bcode = 0x7fffffff; float4 wsel = w0;     // NaN distances only: the first candidate
-      auto consider = [&](float d, float nrm, int code, const float4& w) {
-        const float e = (rr - 2.f * d) + nrm;
-        if (code >= 0 && (e < best || (e == best && code < bcode))) { best = e; bcode = code; wsel = w; }
-      };
-      consider(d0, n0, cd.x, w0); consider(d1, n1, cd.y, w1); consider(d2, n2, cd.z, w2); consider(d3, n3, cd.w, w3);
-      if (bcode == 0x7fffffff) bcode = cd.x;
-      *reinterpret_cast<float4*>(rp) = sub_row<TRAIN>(p, rl, wsel);
-      const int64_t nfr = tile_n0 + f;
-      if (lane == 0) {
-        *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;
-        if (f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
-      }
-    }
+    for (int i = u; i < nslow; i += kUpdWarps) { item_load(i, it); item_finish(it); }
     // wide candidate sets: one frame per warp at a time, handed out from the last warp down
     #pragma unroll 1
     for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
@@ -455,30 +461,53 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   }
   const bool doneA = nA >= 2 && nA <= 4, doneB = nB >= 2 && nB <= 4;     // already updated by the resolving quarter-warp
   RVQ_TRACE3(trX, trn, u, 3);
+  // Phase 1 (on the chain to the next stage's MMA): n = r - q in registers (the winner rows are overwritten), fp16 operand
+  // to tensor memory, a_ready.  Phase 2 (off that chain): residual rows back to shared memory, exact rounding residue of
+  // the operand, squared error; the caller publishes it on dr_ready, which the score warps await before their winner phase.
   uint32_t w[32];
+  auto sub_pack = [&](int f, float4 (&qr)[8], int half, bool done) {
+    const int sw = rs_swz(f);
+    const float* rbase = rs + f * 128 + ((m ^ (sw & 3)) << 2);
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 rv = *reinterpret_cast<const float4*>(rbase + ((i ^ (sw >> 2)) << 4));
+      const float4 n = done ? rv : sub_row<TRAIN>(p, rv, qr[i]);
+      qr[i] = n;
+      w[4 * i + 2 * half] = pack_half2(n.x, n.y);
+      w[4 * i + 2 * half + 1] = pack_half2(n.z, n.w);
+    }
+  };
+  sub_pack(fA, qa, 0, doneA);
+  RVQ_TRACE3(trX, trn, u, 4);
+  sub_pack(fB, qb, 1, doneB);
+  RVQ_TRACE3(trX, trn, u, 5);
+  if (store) {
+    ptx::tmem_st_16x256b_x8(taddr, w);
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar_a);
+  }
+  RVQ_TRACE3(trX, trn, u, 6);
   float e2a, e2b;
-  auto process = [&](int f, const float4 (&qr)[8], int half, float& e2, bool done) {
+  auto finish = [&](int f, const float4 (&nr)[8], int half, float& e2) {
     const int sw = rs_swz(f);
     float* rbase = rs + f * 128 + ((m ^ (sw & 3)) << 2);
     float e[4] = {0.f, 0.f, 0.f, 0.f};
     float sqf = 0.f;
     #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4* rp = reinterpret_cast<float4*>(rbase + ((i ^ (sw >> 2)) << 4));
-      const float4 rv = *rp;
-      const float4 n = done ? rv : sub_row<TRAIN>(p, rv, qr[i]);
-      *rp = n;
-      e[i & 3] = residue2(n.x, n.y, w[4 * i + 2 * half], e[i & 3]);
-      e[i & 3] = residue2(n.z, n.w, w[4 * i + 2 * half + 1], e[i & 3]);
+      const float4 n = nr[i];
+      *reinterpret_cast<float4*>(rbase + ((i ^ (sw >> 2)) << 4)) = n;
+      e[i & 3] = residue_of(n.x, n.y, w[4 * i + 2 * half], e[i & 3]);
+      e[i & 3] = residue_of(n.z, n.w, w[4 * i + 2 * half + 1], e[i & 3]);
       if (TRAIN) sqf = dot4(n, n, sqf);
     }
     e2 = (e[0] + e[1]) + (e[2] + e[3]);
     if (TRAIN && f < p.tf && tile_n0 + f < p.N) sq += sqf;      // sum((q - r)^2) of core_vq.py:319 = |new residual|^2
   };
-  process(fA, qa, 0, e2a, doneA);
-  RVQ_TRACE3(trX, trn, u, 4);
-  process(fB, qb, 1, e2b, doneB);
-  RVQ_TRACE3(trX, trn, u, 5);
+  finish(fA, qa, 0, e2a);
+  finish(fB, qb, 1, e2b);
   // exact rounding residue of the new operand rows: sum over the 4 lanes of the group
   e2a += __shfl_xor_sync(0xffffffffu, e2a, 1); e2b += __shfl_xor_sync(0xffffffffu, e2b, 1);
   e2a += __shfl_xor_sync(0xffffffffu, e2a, 2); e2b += __shfl_xor_sync(0xffffffffu, e2b, 2);
@@ -487,7 +516,6 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     dr2[fA] = e2a; dr2[kM + fA] = 0.f;
     dr2[fB] = e2b; dr2[kM + fB] = 0.f;
   }
-  if (store) ptx::tmem_st_16x256b_x8(taddr, w);
   RVQ_TRACE3(trX, trn, u, 6);
 }
 
@@ -514,7 +542,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) { ptx::mbar_init(RVQ_BAR(full, i), 1); ptx::mbar_init(RVQ_BAR(empty, i), 1); }
     for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(RVQ_BAR(acc_full, i), 1); ptx::mbar_init(RVQ_BAR(acc_empty, i), 4); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(RVQ_BAR(a_ready, i), kUpdWarps); ptx::mbar_init(RVQ_BAR(cand_ready, i), 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(RVQ_BAR(a_ready, i), kUpdWarps); ptx::mbar_init(RVQ_BAR(cand_ready, i), 4);
+                                  ptx::mbar_init(RVQ_BAR(dr_ready, i), kUpdWarps); }
     ptx::fence_mbar_init();
   }
   if (threadIdx.x < 2) {
@@ -669,7 +698,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(RVQ_BAR(a_ready, X));
+      if (lane == 0) { ptx::mbar_arrive(RVQ_BAR(a_ready, X)); ptx::mbar_arrive(RVQ_BAR(dr_ready, X)); }
     };
     // n = -1 is the prologue: it only loads the first tile of each slot (one call site for the tile load)
     for (int n = -1; n < steps0; ++n) {
@@ -694,7 +723,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           float sq = 0.f;
           // operand rows of this warp: TMEM lanes 32q + 16h .. +15, columns of slot X
           update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st),
-                             tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, sq, X, n,
+                             tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, RVQ_BAR(a_ready, X), sq, X, n,
 #ifdef RVQ_TC_TRACE
                              t_kernel0
 #else
@@ -705,10 +734,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           RVQ_TRACE(X, n, 7, u == 0 && lane == 0);
           if (threadIdx.x == 128) { int* qc = reinterpret_cast<int*>(ms + Sm::m_qcnt); qc[0] = 0; qc[1] = 0; }
           if (!last) {
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(RVQ_BAR(a_ready, X));
+            if (lane == 0) ptx::mbar_arrive(RVQ_BAR(dr_ready, X));      // residual rows, rounding residues and queue reset are in place
             RVQ_TICK(t_stw);
             RVQ_TRACE(X, n, 8, u == 0 && lane == 0);
           } else {
@@ -775,68 +802,44 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         for (int j = 0; j < 32; ++j) { cm[j] = inf_f(); bmin[j] = inf_f(); }
         // one rolled iteration per 128-code chunk (the hot loops of a stage must stay inside the instruction cache);
         // bmin is a shift register: after the loop the a-th batch in processing order sits at 32 - 4*nchunks + a
-        // The 128 columns of a chunk are read as four groups of 2 x 16 columns, G0 = {0-15, 32-47}, G1 = {16-31, 48-63},
-        // G2 = {64-79, 96-111}, G3 = {80-95, 112-127} (16 classes of two batches each), into two register sets: while one
-        // set is reduced the other one's tcgen05.ld is in flight, across chunk boundaries too.
-        uint32_t pa[16], pb[16], qa[16], qb[16];
-        auto ld_group = [&](uint32_t buf, int g, uint32_t (&x0)[16], uint32_t (&x1)[16]) {
-          const uint32_t col = tlane + buf * kN + (g >> 1) * 64 + (g & 1) * 16;
-          ptx::tmem_ld16(col, x0);
-          ptx::tmem_ld16(col + 32, x1);
-        };
-        // class minima of the group's 16 classes (offset o) and the two partial batch minima (h0: first batch, h1: second)
-        auto reduce_group = [&](const uint32_t (&x0)[16], const uint32_t (&x1)[16], int o, float& h0, float& h1) {
-          #pragma unroll
-          for (int j = 0; j < 16; ++j) cm[o + j] = ptx::fmin3(cm[o + j], __uint_as_float(x0[j]), __uint_as_float(x1[j]));
-          h0 = min16(x0);
-          h1 = min16(x1);
-        };
-        uint32_t buf = acc_it % kAccBufs;
-        ptx::mbar_wait(RVQ_BAR(acc_full, buf), (acc_it / kAccBufs) & 1);
-        ptx::tc_fence_after();
-        ++acc_it;
-        RVQ_TICK(t_wait);
-        RVQ_TRACE(X, n, 3, warp == 0 && lane == 0);
-        ld_group(buf, 0, pa, pb);
-        ld_group(buf, 1, qa, qb);
         #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
+          const uint32_t buf = acc_it % kAccBufs, aph = (acc_it / kAccBufs) & 1;
+          ++acc_it;
+          ptx::mbar_wait(RVQ_BAR(acc_full, buf), aph);
+          ptx::tc_fence_after();
+          RVQ_TICK(t_wait);
+          if (c == 0) RVQ_TRACE(X, n, 3, warp == 0 && lane == 0);
           if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c);
-          float h0, h1, g0, g1;
+          uint32_t v0[32], v1[32];
+          ptx::tmem_ld32(tlane + buf * kN, v0);
+          ptx::tmem_ld32(tlane + buf * kN + 32, v1);
           #pragma unroll
           for (int j = 0; j < 28; ++j) bmin[j] = bmin[j + 4];
-          ptx::tmem_ld_wait();                                   // G0, G1
-          reduce_group(pa, pb, 0, h0, h1);
-          ld_group(buf, 2, pa, pb);
-          reduce_group(qa, qb, 16, g0, g1);
-          bmin[28] = fminf(h0, g0);
-          bmin[29] = fminf(h1, g1);
-          ptx::tmem_ld_wait();                                   // G2
-          ld_group(buf, 3, qa, qb);
-          reduce_group(pa, pb, 0, h0, h1);
-          ptx::tmem_ld_wait();                                   // G3: the whole chunk is in registers, hand the accumulator back
+          ptx::tmem_ld_wait();
+          #pragma unroll
+          for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+          bmin[28] = min32(v0);
+          bmin[29] = min32(v1);
+          ptx::tmem_ld32(tlane + buf * kN + 64, v0);
+          ptx::tmem_ld32(tlane + buf * kN + 96, v1);
+          ptx::tmem_ld_wait();
+          // scores are in registers: hand the accumulator back before reducing them
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(RVQ_BAR(acc_empty, buf));
           if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c + 1);
-          const bool more = c + 1 < nchunks;
-          if (more) {                                            // next chunk's G0 flies while G3 is reduced
-            buf = acc_it % kAccBufs;
-            ptx::mbar_wait(RVQ_BAR(acc_full, buf), (acc_it / kAccBufs) & 1);
-            ptx::tc_fence_after();
-            ++acc_it;
-            ld_group(buf, 0, pa, pb);
-          }
-          reduce_group(qa, qb, 16, g0, g1);
-          if (more) ld_group(buf, 1, qa, qb);
-          bmin[30] = fminf(h0, g0);
-          bmin[31] = fminf(h1, g1);
+          #pragma unroll
+          for (int j = 0; j < 32; ++j) cm[j] = ptx::fmin3(cm[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+          bmin[30] = min32(v0);
+          bmin[31] = min32(v1);
           RVQ_TICK(t_epi);
           if (warp == 0 && lane == 0) RVQ_TRACE2(X, n, 64 + 3 * c + 2);
         }
         RVQ_TRACE(X, n, 4, warp == 0 && lane == 0);
         // |x|^2 of a new tile and the rounding residue of this frame's operand were written by the update warps; the
         // scores above could only exist after they had finished
+        ptx::mbar_wait(RVQ_BAR(dr_ready, X), uint32_t(n) & 1);          // (completed long ago: the update warps finish phase 2 during the MMAs)
         float xx = X ? xx_1 : xx_0;
         if (s == 0) xx = reinterpret_cast<const float*>(ms + Sm::m_cmask)[f] + reinterpret_cast<const float*>(ms + Sm::m_bmask)[f];
         const float xnorm = sqrtf(xx);
@@ -865,11 +868,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         const int nc = __popc(cmask), nb = __popc(bmask);
         const bool full = outl || cmask == 0u || bmask == 0u;     // masks are empty only for NaN scores
         const int ncand = nc * nb;
-        // bmask bit a = a-th batch in this CTA's processing order; its codes start at batch_base(a)
-        auto batch_base = [&](int a) { int pc = (a >> 2) + rot; pc = pc < nchunks ? pc : pc - nchunks; return pc * 128 + (a & 3) * 32; };
+        // bmask bit a = a-th batch in this CTA's processing order (code_of)
+
         // first candidate (= the winner when certified); the update warps enumerate the other codes of a short list
         // from the two masks
-        const int4 cd = make_int4(batch_base(__ffs(bmask) - 1) + (__ffs(cmask) - 1), -1, -1, -1);
+        const int4 cd = make_int4(code_of(__ffs(bmask) - 1, __ffs(cmask) - 1, rot, nchunks), -1, -1, -1);
         *reinterpret_cast<int4*>(ms + Sm::m_cand + f * 16) = cd;
         *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
         *reinterpret_cast<uint32_t*>(ms + Sm::m_cmask + f * 4) = cmask;

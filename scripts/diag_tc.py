@@ -19,8 +19,12 @@ def timed(fn, n=10):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
+import bench as _bench
 for nq in sorted({1, 8, NQ}):
-    t_tc = timed(lambda: ops.encode(pk, x, 0, nq))
+    sampler = _bench.ClockSampler(_bench._physical_gpu_index(0), period=0.002)
+    sampler.start()
+    t_tc = timed(lambda: ops.encode(pk, x, 0, nq), n=10 if nq < NQ else 100)
+    clk = sampler.stop()
     st = ops.search_stats(pk)
     c1 = ops.encode(pk, x, 0, nq)[0]; c2 = ops.encode(pk, x, 0, nq, flags=L.FLAG_FORCE_EXACT)[0]
     N = B * T
@@ -28,7 +32,7 @@ for nq in sorted({1, 8, NQ}):
     ctas = min(148, tiles)
     ts = tiles * nq                      # tile-stages in the launch
     print(f"n_q={nq}: tc {t_tc:.3f} ms ({t_tc*1e-3*1.965e9/ (-(-tiles//ctas)*nq):.0f} cyc per tile-stage of the longest CTA), "
-          f"certified {st['certified']}/{st['searched']}, rescored {st['rescored']}, fullscan {st['fullscan']}, mismatches vs exact {(c1 != c2).sum().item()}")
+          f"certified {st['certified']}/{st['searched']}, rescored {st['rescored']}, fullscan {st['fullscan']}, mismatches vs exact {(c1 != c2).sum().item()}, sm clock {clk['sm_mhz']} MHz {clk['reasons']}")
     if st["warps"]:
         w = st["warps"]                  # score warps counted = 4 per CTA
         per = lambda k, div: st[k] / div
