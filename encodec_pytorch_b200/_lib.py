@@ -37,6 +37,8 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "rvq_ema_apply": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _dbl, _dbl, _vp]),
     "rvq_expire_replace": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "rvq_expire_codes": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _vp]),
+    "rvq_expire_stack": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _f, C.c_uint64, C.c_uint64,
+                               _vp, _vp, _i, _vp]),
     "rvq_kmeans_assign": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp]),
     "rvq_kmeans_update": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "rvq_residual_combine": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),

@@ -173,6 +173,32 @@ def expire_codes(pk: CodebookPack, x: torch.Tensor, codes: torch.Tensor, stage0:
                                      embed.data_ptr(), flags, L.stream_ptr(x.device)), "rvq_expire_codes")
 
 
+def expire_stack(pk: CodebookPack, x: torch.Tensor, codes: torch.Tensor, stage0: int,
+                 cluster_sizes: tp.Sequence[torch.Tensor], embeds: tp.Sequence[torch.Tensor], threshold: float,
+                 seed: int, offset: int, flags: int = 0) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+    """Dead-code expiry of ``len(embeds)`` stages in two launches and no host sync (``rvq_expire_stack``).
+    Returns ``(sel [n, K] int64, fired [n] int32)``: the drawn frame numbers and the per-stage "any code
+    below threshold" flags, both on the device."""
+    lib = L.load()
+    L.require_cuda_f32(x, "x")
+    B, D, T = (int(v) for v in x.shape)
+    n = len(embeds)
+    for t in (*cluster_sizes, *embeds):
+        L.require_cuda_f32(t, "codebook buffer")
+        if not t.is_contiguous():
+            raise RuntimeError("codebook buffers must be contiguous")
+    assert codes.is_contiguous() and len(cluster_sizes) == n
+    sel = torch.empty((n, pk.K), dtype=torch.int64, device=x.device)
+    fired = torch.empty((n,), dtype=torch.int32, device=x.device)
+    sb, sd, st = _strides_bdt(x)
+    with _guard(x.device):
+        L.check(lib.rvq_expire_stack(pk.buf.data_ptr(), pk.K, pk.D, x.data_ptr(), sb, sd, st, B, T, stage0, n,
+                                     codes.data_ptr(), L.ptr_array(cluster_sizes), L.ptr_array(embeds), float(threshold),
+                                     int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), sel.data_ptr(), fired.data_ptr(),
+                                     flags, L.stream_ptr(x.device)), "rvq_expire_stack")
+    return sel, fired
+
+
 def kmeans_assign(pk: CodebookPack, samples: torch.Tensor) -> torch.Tensor:
     lib = L.load()
     L.require_cuda_f32(samples, "samples")

@@ -559,6 +559,104 @@ expire_codes_kernel(const unsigned char* pack, int K, int D, const float* __rest
   }
 }
 
+// ---- expiry of a whole residual stack without a host round trip (core_vq.py:165-175 for n stages) ----------------
+// counter-based generator for the index draw: 64-bit finalizer of (seed, offset, stage, slot, round)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ int64_t draw_index(uint64_t seed, uint64_t offset, int stage, int slot, int round, int64_t N) {
+  const uint64_t r = mix64(mix64(seed ^ mix64(offset + uint64_t(stage))) ^ (uint64_t(slot) << 24) ^ uint64_t(round));
+  return int64_t(__umul64hi(r, uint64_t(N)));             // uniform on [0, N) up to 2^-64 N
+}
+constexpr int kSelTable = 4096;                           // hash set of the draws of one stage (K <= kSelTable / 2)
+
+// One block per stage.  fired[stage] = any(cluster_size < thr) (the reference's host-side torch.any, :168-170); for a
+// firing stage, sel[stage, 0..K) = K distinct frame numbers, uniformly random and in random order -- the distribution
+// of randperm(N)[:K] (sample_vectors, :69-77) -- or K draws with replacement when N < K (:75).  Duplicate draws are
+// settled deterministically (lowest (round, slot) keeps the value, the others draw again), so a (seed, offset) pair
+// reproduces the same indices.
+__global__ void __launch_bounds__(1024)
+expire_sample_kernel(PtrTable32 cs_tab, int stage_base, int K, int64_t N, float thr, uint64_t seed, uint64_t offset,
+                     int64_t* __restrict__ sel, int* __restrict__ fired) {
+  __shared__ unsigned keys[kSelTable];
+  __shared__ int owner[kSelTable];
+  const int tid = threadIdx.x, stage = stage_base + blockIdx.x;
+  const float* cs = cs_tab.p[blockIdx.x];
+  int dead = 0;
+  for (int k = tid; k < K; k += blockDim.x) dead |= (cs[k] < thr) ? 1 : 0;
+  dead = __syncthreads_or(dead);
+  if (tid == 0) fired[stage] = dead;
+  if (!dead) return;
+  int64_t* out = sel + int64_t(stage) * K;
+  if (N < K) {
+    for (int k = tid; k < K; k += blockDim.x) out[k] = draw_index(seed, offset, stage, k, 0, N);
+    return;
+  }
+  int M = 64;
+  while (M < 2 * K) M <<= 1;                              // <= kSelTable (checked by the host entry)
+  for (int i = tid; i < M; i += blockDim.x) { keys[i] = 0xffffffffu; owner[i] = 0x7fffffff; }
+  __syncthreads();
+  bool done[2] = {false, false};                          // slots tid, tid + 1024
+  for (int round = 0;; ++round) {
+    unsigned v[2] = {0u, 0u}; int h[2] = {0, 0};
+    #pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = tid + j * 1024;
+      if (k >= K || done[j]) continue;
+      v[j] = unsigned(draw_index(seed, offset, stage, k, round, N));
+      int hh = int((v[j] * 2654435761u) >> 7) & (M - 1);
+      for (;;) {
+        const unsigned prev = atomicCAS(&keys[hh], 0xffffffffu, v[j]);
+        if (prev == 0xffffffffu || prev == v[j]) break;
+        hh = (hh + 1) & (M - 1);
+      }
+      atomicMin(&owner[hh], (round << 12) | k);
+      h[j] = hh;
+    }
+    __syncthreads();
+    int pending = 0;
+    #pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = tid + j * 1024;
+      if (k >= K || done[j]) continue;
+      if (owner[h[j]] == ((round << 12) | k)) { done[j] = true; out[k] = int64_t(v[j]); }
+      else pending = 1;
+    }
+    if (!__syncthreads_or(pending)) break;
+  }
+}
+
+// one warp per (stage, code k): a dead code takes the stage's input residual of frame sel[stage, k], recomputed from x and
+// the codes with the encode arithmetic
+__global__ void __launch_bounds__(256)
+expire_stack_kernel(const unsigned char* pack, int K, int D, const float* __restrict__ x, rvq::FrameAddr fa, int64_t N,
+                    int stage0, int stage_base, const int64_t* __restrict__ codes, const int64_t* __restrict__ sel,
+                    const int* __restrict__ fired, PtrTable32 cs_tab, MutPtrTable32 em_tab, float thr, int ste) {
+  const int rel = blockIdx.y, stage = stage_base + rel;   // stage: relative to stage0
+  if (!fired[stage]) return;
+  rvq::PackView pv(pack, K, D);
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= K || !(cs_tab.p[rel][k] < thr)) return;
+  int64_t n = sel[int64_t(stage) * K + k];
+  n = n < 0 ? 0 : (n >= N ? N - 1 : n);
+  float* embed = em_tab.p[rel];
+  for (int d = lane; d < D; d += 32) {
+    float r = x[fa.base(n) + int64_t(d) * fa.sxd];
+    for (int i = 0; i < stage; ++i) {
+      int64_t c = codes[int64_t(i) * N + n];
+      int idx = c < 0 ? 0 : (c >= K ? K - 1 : int(c));
+      float q = pv.tab32(stage0 + i)[size_t(idx) * D + d];
+      if (ste) q = r + (q - r);
+      r -= q;
+    }
+    embed[size_t(k) * D + d] = r;
+  }
+}
+
 __global__ void kmeans_scatter_kernel(const float* __restrict__ samples, int64_t N, int D,
                                       const int64_t* __restrict__ buckets, int K,
                                       float* sums, unsigned long long* bins) {
@@ -687,6 +785,35 @@ int rvq_expire_codes(const void* pack, int K, int D, const float* x, int64_t sxb
                                                                      stage, codes, sel, cluster_size, threshold, embed,
                                                                      (flags & RVQ_FLAG_STE) ? 1 : 0);
   RVQ_LAUNCH_CHECK("expire_codes_kernel");
+  return RVQ_OK;
+}
+
+int rvq_expire_stack(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+                     int B, int T, int stage0, int n_q, const int64_t* codes,
+                     const float* const* cluster_size_ptrs_host, float* const* embed_ptrs_host, float threshold,
+                     uint64_t seed, uint64_t offset, int64_t* sel, int* fired, int flags, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(pack && x && sel && fired && cluster_size_ptrs_host && embed_ptrs_host && (codes || n_q <= 1),
+              "rvq_expire_stack: null pointer");
+  RVQ_REQUIRE(K > 0 && 2 * K <= kSelTable && D > 0 && n_q >= 0 && stage0 >= 0, "rvq_expire_stack: bad shape (K=%d)", K);
+  const int64_t N = int64_t(B) * T;
+  RVQ_REQUIRE(N > 0 && N < (int64_t(1) << 31), "rvq_expire_stack: frame count out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  FrameAddr fa{sxb, sxd, sxt, T};
+  for (int s0 = 0; s0 < n_q; s0 += 32) {
+    const int ns = n_q - s0 < 32 ? n_q - s0 : 32;
+    PtrTable32 cs;
+    MutPtrTable32 em;
+    for (int i = 0; i < 32; ++i) {
+      cs.p[i] = i < ns ? cluster_size_ptrs_host[s0 + i] : nullptr;
+      em.p[i] = i < ns ? embed_ptrs_host[s0 + i] : nullptr;
+    }
+    expire_sample_kernel<<<ns, 1024, 0, st>>>(cs, s0, K, N, threshold, seed, offset, sel, fired);
+    RVQ_LAUNCH_CHECK("expire_sample_kernel");
+    expire_stack_kernel<<<dim3((K + 7) / 8, ns), 256, 0, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0, s0, codes,
+                                                             sel, fired, cs, em, threshold, (flags & RVQ_FLAG_STE) ? 1 : 0);
+    RVQ_LAUNCH_CHECK("expire_stack_kernel");
+  }
   return RVQ_OK;
 }
 

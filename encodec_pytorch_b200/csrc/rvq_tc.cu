@@ -376,7 +376,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   // handful of registers next to the winner rows in flight.  Exact fp32 distances (core_vq.py:183-187), lowest code on
   // ties; the warp holds the winner's row and applies r <- r - q itself.
   struct Item { int f; int4 cd; float* rp; float4 rl, w0, w1, w2, w3; float n0, n1, n2, n3; };
-  auto item_load = [&](int i, Item& it) {
+  auto item_cands = [&](int i, Item& it) {
     it.f = slowq[i];
     // the 2..4 candidates = flagged batches x flagged classes (warp-uniform enumeration; bit a of the batch mask is the
     // a-th batch in this CTA's processing order)
@@ -393,6 +393,9 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
         ++w;
       }
     }
+  };
+  auto item_load = [&](int i, Item& it) {
+    item_cands(i, it);
     it.rp = rs + rs_off(it.f, lane);
     it.rl = *reinterpret_cast<const float4*>(it.rp);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -974,8 +977,9 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   if (const char* e = getenv("RVQ_TC_TILE_FRAMES")) { const int v = atoi(e); if (v >= 1 && v <= kM) tf = v; }   // tuning knob
   p.tf = int(tf);
   const int64_t ntiles = (N + tf - 1) / tf;
-  const int64_t want = (ntiles + 1) / 2;
-  const unsigned grid = unsigned(want < sm_count ? want : sm_count);
+  // one tile per CTA while there are SMs to spare (a lone tile's stage is shorter than a pair's: small calls are latency-bound),
+  // two or more tiles per CTA beyond that
+  const unsigned grid = unsigned(ntiles < sm_count ? ntiles : sm_count);
   // the lean variant serves plain encodes; straight-through arithmetic, loss numerators and the residual output
   // live in the other one (a stage's hot code has to fit the instruction cache)
   if (p.ste || p.sqerr != nullptr || p.residual_out != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, Sm::total, st>>>(p);

@@ -339,14 +339,32 @@ def _warn_issue25() -> None:
                   'The bug wasn\'t fixed here for reproducibility.')
 
 
+def _rng_stream(device: torch.device, n: int) -> tp.Tuple[int, int]:
+    """(seed, offset) of the device's global torch generator for a device-side draw, advancing it like a
+    torch random op would (``torch.manual_seed`` therefore reproduces the draws)."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(off + 4 * max(1, n))
+    return seed, off
+
+
 def _expire_stack(layers: tp.Sequence[VectorQuantization], pk: ops.CodebookPack, x: torch.Tensor,
                   codes: torch.Tensor, stage0: int, flags: int) -> None:
-    """Dead-code expiry (core_vq.py:165-175) for a run of stages: one host read of the per-stage
-    "any code below threshold" flags (the reference syncs once per stage), then for each firing
-    stage, in stage order, the reference's index draw and ``rvq_expire_codes``."""
+    """Dead-code expiry (core_vq.py:165-175) for a run of stages.  The reference reads ``torch.any(expired)``
+    on the host and draws ``randperm`` once per stage; here the "any" test, the index draw (same law:
+    K distinct uniformly random frames in random order) and the row replacement of every stage run on the
+    device in two launches, with no host sync (``rvq_expire_stack``).  Codebooks larger than the kernel's
+    draw table keep the stage-by-stage path."""
     cbs = [l._codebook for l in layers]
     thr = cbs[0].threshold_ema_dead_code
     if thr == 0:
+        return
+    if 2 * cbs[0].codebook_size <= 4096:
+        seed, off = _rng_stream(x.device, len(cbs))
+        ops.expire_stack(pk, x, codes, stage0, [cb.cluster_size for cb in cbs], [cb.embed for cb in cbs],
+                         float(thr), seed, off, flags)
+        for cb in cbs:
+            cb._tables_changed()
         return
     flags_host = torch.stack([(cb.cluster_size < thr).any() for cb in cbs]).tolist()
     b, _, t = x.shape

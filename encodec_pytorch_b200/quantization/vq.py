@@ -58,7 +58,9 @@ class ResidualVectorQuantizer(nn.Module):
         bw_per_q = self.get_bandwidth_per_quantizer(sample_rate)
         n_q = self.get_num_quantizers_for_bandwidth(sample_rate, bandwidth)
         quantized, codes, commit_loss = self.vq(x, n_q=n_q)
-        bw = torch.tensor(n_q * bw_per_q).to(x)
+        # == torch.tensor(n_q * bw_per_q).to(x) (vq.py:94), built on the device: the pageable host-to-device copy of the
+        # reference form synchronises the stream
+        bw = torch.full((), n_q * bw_per_q, dtype=x.dtype, device=x.device)
         return QuantizedResult(quantized, codes, bw, penalty=torch.mean(commit_loss))
 
     def get_num_quantizers_for_bandwidth(self, sample_rate: int, bandwidth: tp.Optional[float] = None) -> int:

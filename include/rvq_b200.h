@@ -115,6 +115,22 @@ int rvq_expire_codes(const void* pack, int K, int D,
                      const float* cluster_size, float threshold, float* embed,
                      int flags, void* stream);
 
+/* ---- expiry of a whole residual stack with no host round trip (core_vq.py:165-175 applied to n_q stages; replaces
+ * the per-stage `torch.any` host sync + `randperm` + rvq_expire_codes sequence).  Per stage i:
+ *   fired[i] = any(cluster_size_i < threshold)                       (int32 [n_q] DEVICE, out)
+ *   sel[i,:] = K distinct frame numbers in [0, B*T), uniformly random and in random order -- the law of
+ *              randperm(N)[:K] (sample_vectors, :69-77); K draws with replacement when B*T < K (:75).  Drawn on the
+ *              device from the counter-based stream (seed, offset); the same pair reproduces the same indices.
+ *              (int64 [n_q, K] DEVICE, out; rows of stages that did not fire are left untouched)
+ *   embed_i[k] <- r_i[sel[i,k]] where cluster_size_i[k] < threshold  (r_i: input residual of stage i, as in
+ *              rvq_expire_codes).  Stages index relative to stage0; *_ptrs_host are HOST arrays of DEVICE pointers.
+ * K <= 2048.                                                                                        */
+int rvq_expire_stack(const void* pack, int K, int D,
+                     const float* x, int64_t sxb, int64_t sxd, int64_t sxt, int B, int T,
+                     int stage0, int n_q, const int64_t* codes,
+                     const float* const* cluster_size_ptrs_host, float* const* embed_ptrs_host, float threshold,
+                     uint64_t seed, uint64_t offset, int64_t* sel, int* fired, int flags, void* stream);
+
 /* ---- k-means (core_vq.py:80-102) on flat fp32 samples [N, D] (contiguous).
  * assign: buckets[n] = argmin_k sum_d (x[n,d]-means[k,d])^2, lowest index on ties (:86-91);
  *         `pack` is an rvq_pack() image (n_q = 1) of the current means.

@@ -429,3 +429,76 @@ def test_full_size_properties(shape):
         c3, _, _, r3 = ops.encode(pk, x, 0, n_q, want_residual=True)
         assert torch.equal(c3, codes)
         assert torch.equal(r3, res)
+
+
+def test_expire_stack_device_draw():
+    """rvq_expire_stack (core_vq.py:165-175 for a whole stack, no host sync): per-stage "any dead code" flags, K distinct
+    in-range frame numbers per firing stage, dead rows <- that stage's input residual of the drawn frame (bit-exact
+    against the residual chain recomputed with torch), live rows and non-firing stages untouched, reproducible draws."""
+    import encodec_pytorch_b200 as E
+    from encodec_pytorch_b200 import _ops as ops
+    torch.manual_seed(3)
+    n_q, K, D = 4, 1024, 128
+    q = E.ResidualVectorQuantizer(dimension=D, n_q=n_q, bins=K, kmeans_init=False).cuda().train()
+    cbs = [l._codebook for l in q.vq.layers]
+    x = torch.randn(2, D, 700, device="cuda")
+    N = 2 * 700
+    cs = [torch.full((K,), 5.0, device="cuda") for _ in range(n_q)]
+    cs[0][::3] = 0.5                     # stage 0: a third of the codes are dead
+    cs[2][7] = 1.0                       # stage 2: one dead code; stages 1 and 3: none
+    for cb, c in zip(cbs, cs):
+        cb.cluster_size.copy_(c)
+    pk = q.vq._stack_pack()
+    codes = ops.encode(pk, x, 0, n_q)[0]
+    before = [cb.embed.clone() for cb in cbs]
+    sel, fired = ops.expire_stack(pk, x, codes, 0, [cb.cluster_size for cb in cbs], [cb.embed for cb in cbs], 2.0, 1234, 8)
+    assert fired.tolist() == [1, 0, 1, 0]
+    # the residual chain of the encode arithmetic: r_0 = x, r_{i+1} = r_i - embed_i[codes_i]
+    r = x.permute(0, 2, 1).reshape(N, D).clone()
+    for i in range(n_q):
+        dead = cs[i] < 2.0
+        if fired[i]:
+            s_i = sel[i]
+            assert int(s_i.min()) >= 0 and int(s_i.max()) < N
+            assert s_i.unique().numel() == K if N >= K else True
+            assert torch.equal(cbs[i].embed[dead], r[s_i[dead]])
+        assert torch.equal(cbs[i].embed[~dead], before[i][~dead])
+        r = r - before[i][codes[i].reshape(N)]
+    # same (seed, offset) -> same draw; another offset -> another draw
+    for cb, b0 in zip(cbs, before):
+        cb.embed.copy_(b0)
+    sel2, _ = ops.expire_stack(pk, x, codes, 0, [cb.cluster_size for cb in cbs], [cb.embed for cb in cbs], 2.0, 1234, 8)
+    assert torch.equal(sel2[0], sel[0]) and torch.equal(sel2[2], sel[2])
+    sel3, _ = ops.expire_stack(pk, x, codes, 0, [cb.cluster_size for cb in cbs], [cb.embed for cb in cbs], 2.0, 1234, 12)
+    assert not torch.equal(sel3[0], sel[0])
+    # fewer frames than codes: draws with replacement (core_vq.py:75), still in range; and the draw is uniform
+    xs = x[:, :, :300].contiguous()
+    cds = ops.encode(pk, xs, 0, n_q)[0]
+    sel4, f4 = ops.expire_stack(pk, xs, cds, 0, [cb.cluster_size for cb in cbs], [cb.embed for cb in cbs], 2.0, 99, 0)
+    assert f4.tolist() == [1, 0, 1, 0] and int(sel4[0].min()) >= 0 and int(sel4[0].max()) < 600
+    big = torch.randn(8, D, 6000, device="cuda")
+    cdb = ops.encode(pk, big, 0, 1)[0]
+    draws = torch.stack([ops.expire_stack(pk, big, cdb, 0, [cbs[0].cluster_size], [cbs[0].embed], 2.0, 7, 4 * j)[0][0]
+                         for j in range(16)]).double() / 48000.0
+    assert abs(float(draws.mean()) - 0.5) < 0.01 and abs(float(draws.var()) - 1.0 / 12.0) < 0.005
+
+
+def test_training_forward_does_not_sync_the_host():
+    """Steady-state training forward (search, quantized sum, losses, expiry, EMA) enqueues work only: with
+    torch.cuda.set_sync_debug_mode('error') any host synchronisation would raise."""
+    import warnings
+    import encodec_pytorch_b200 as E
+    torch.manual_seed(0)
+    q = E.ResidualVectorQuantizer(dimension=128, n_q=8, bins=1024, kmeans_init=False).cuda().train()
+    x = torch.randn(4, 128, 300, device="cuda")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.no_grad():
+            q(x, 75, 6.0)                                  # builds the pack / scratch
+            torch.cuda.synchronize()
+            torch.cuda.set_sync_debug_mode("error")
+            try:
+                r = q(x, 75, 6.0)
+            finally:
+                torch.cuda.set_sync_debug_mode("default")
+    assert r.codes.shape == (8, 4, 300) and torch.isfinite(r.penalty)
