@@ -30,8 +30,9 @@ UNIT = "frames/s"
 B, D, T, NQ, BINS, FRAME_RATE, BW = 64, 128, 750, 32, 1024, 75, 24.0
 FLOP_PER_FRAME_STAGE = 2 * BINS * D          # only the x.c^T contraction counts
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_encode_kernel launch at cfg2 (ncu --set full,
-# profiles/r1c_tc_encode_ncu_raw.csv): 51.25 MB + 2.62 MB; algorithmic: 24.6 MB latents + 12.3 MB codes (+ first touch of the pack)
-NCU_DRAM_BYTES_PER_LAUNCH = 53.87e6
+# profiles/r1e_tc_encode_ncu_raw.csv): 51.22 MB + 1.83 MB; algorithmic: 24.6 MB latents + 12.3 MB codes (reads: + first touch of
+# the 43 MB pack, which then stays in L2; writes: the int64 codes mostly still sit dirty in the 126 MB L2 at kernel end)
+NCU_DRAM_BYTES_PER_LAUNCH = 53.05e6
 WORKLOAD = f"cfg2: 24 kHz 24 kbps RVQ encode, latents [{B},{D},{T}] fp32, n_q={NQ}, bins={BINS}"
 
 

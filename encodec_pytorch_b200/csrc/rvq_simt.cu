@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   const int s = stage_base + blockIdx.x;
   PackView pv(pack, K, D);
   const float* t32 = pv.tab32(s);
+  const float* tT = pv.tab32T(s);
   float* cn = const_cast<float*>(pv.cnorm(s));
   const bool tc = tc_shape(K, D);
   int Kp = 1; while (Kp < K) Kp <<= 1;
@@ -64,9 +65,11 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
     float nv = __int_as_float(0x7f800000);
     if (k < K) {
-      const float* row = t32 + size_t(k) * D;
+      // element (k, d) read from the transposed copy: consecutive threads touch consecutive addresses; the sum runs over d
+      // in the same order as before
+      const float* col = tT + k;
       float acc = 0.f, amax = 0.f;
-      for (int d = 0; d < D; ++d) { float v = row[d]; acc = fmaf(v, v, acc); amax = fmaxf(amax, fabsf(v)); }
+      for (int d = 0; d < D; ++d) { float v = col[size_t(d) * K]; acc = fmaf(v, v, acc); amax = fmaxf(amax, fabsf(v)); }
       cn[k] = acc;
       nv = sqrtf(acc);
       // range flags for the fp16 image: B holds -2c, the augmented column holds |c|^2
@@ -112,9 +115,9 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       else {
         lcref = fmaxf(lcref, nv);
         // exact rounding residue of this code's fp16 operand row (-2c): |b - fp16(b)|^2
-        const float* row = t32 + size_t(k) * D;
+        const float* col = tT + k;
         float e2 = 0.f;
-        for (int d = 0; d < D; ++d) { const float b = -2.f * row[d]; const float e = b - __half2float(__float2half_rn(b)); e2 = fmaf(e, e, e2); }
+        for (int d = 0; d < D; ++d) { const float b = -2.f * col[size_t(d) * K]; const float e = b - __half2float(__float2half_rn(b)); e2 = fmaf(e, e, e2); }
         ldb2 = fmaxf(ldb2, e2);
       }
     }
