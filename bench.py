@@ -183,6 +183,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     peaks = _peaks()
 

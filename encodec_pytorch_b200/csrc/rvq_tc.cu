@@ -16,15 +16,17 @@
 //                slots (6 K-groups = 12 KB each; small slots keep more bytes in flight than whole chunks would);
 //            D = 3 accumulator buffers of 128 TMEM columns shared by both slots.
 //   warps    0..3   score warps  (thread = TMEM lane = frame): tcgen05.ld, per-class / per-batch minima, certified
-//                   winner or candidate list (see below), codes of certified frames;
-//            4..11  update warps: gather of the winners' fp32 rows ("lane = dimension", a quarter-warp per frame, four
-//                   rows in flight per quarter-warp), exact fp32 re-score of candidate lists, r <- r - q; then, thread =
-//                   frame, the fp16 operand of the next stage goes to tensor memory (tcgen05.st) together with its
-//                   exact rounding residue; tile loads;
+//                   winner or class/batch masks of the candidates (see below), codes of certified frames;
+//            4..11  update warps, in the order of what sits on the chain to the next stage's MMA: (1) winner rows of the
+//                   certified frames requested from the fp32 table (4 lanes own 2 frames, lane m = 16-byte chunks 4i+m);
+//                   (2) while they fly, frames with a candidate list are settled by a warp each (exact fp32 re-score, the
+//                   warp applies r <- r - q itself); (3) r - q in registers -> fp16 operand of the next stage to tensor
+//                   memory (one tcgen05.st.16x256b.x8) -> a_ready; (4) off the chain: residual rows back to shared
+//                   memory, exact rounding residue of the operand, squared error -> dr_ready; tile loads;
 //            12  TMA producer;  13..15  MMA issuers, chunks round-robin (13 owns the TMEM allocation).
 //            setmaxnreg: 152 registers for the score warps, 160 for the update warps, 40 for the last warpgroup.
 //   sync     mbarriers only between roles: a_ready[slot] (update -> MMA), acc_full/acc_empty (MMA <-> score),
-//            cand_ready[slot] (score -> update), full/empty (TMA <-> MMA).
+//            cand_ready[slot] (score -> update), dr_ready[slot] (update -> score), full/empty (TMA <-> MMA).
 //
 // Certified argmin: a score warp keeps per frame the minimum over every 32-code batch and over every residue class
 // (code mod 32).  A code is within `delta` of the minimum iff its batch AND its class are; delta bounds the fp16
@@ -81,7 +83,8 @@ static_assert(Sm::total <= 227 * 1024, "shared memory budget");
 static_assert(kTcKPad / 16 == 9 && kN == 128 && kTmemA + 2 * 64 == 512, "operand geometry");
 static_assert((Sm::m_size % 16) == 0 && (Sm::misc % 16) == 0, "alignment");
 
-// debug timeline of CTA 0 (slots 0/1, steps kTraceN0 .. kTraceN0 + kTraceSteps - 1): g_trace[X][step][event] = cycles since kernel start
+// debug timeline of CTA 0 (RVQ_TC_TRACE builds; slots 0/1, steps kTraceN0 .. kTraceN0 + kTraceSteps - 1; -DRVQ_TRACE_N0=36
+// looks at the CTA's third tile, which runs alone): g_trace[X][step][event] = cycles since kernel start
 #ifndef RVQ_TRACE_N0
 #define RVQ_TRACE_N0 2
 #endif

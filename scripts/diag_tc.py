@@ -41,3 +41,7 @@ for nq in sorted({1, 8, NQ}):
         print(f"   update warp / tile-stage: wait cand {per('cyc_resolve', uw)*ctas/ts:.0f}  update {per('cyc_update', uw)*ctas/ts:.0f}  operand->tmem {per('cyc_pairbar', uw)*ctas/ts:.0f} + st wait {per('tma_late_lat_sum', uw)*ctas/ts:.0f}  tile loads (per CTA) {per('cyc_load', uw):.0f}")
         print(f"      update split: setup {per('cand2', uw)*ctas/ts:.0f}  own frames {per('cand3_4', uw)*ctas/ts:.0f}  lists {per('cand5_8', uw)*ctas/ts:.0f}  wide {per('cand9plus', uw)*ctas/ts:.0f}  barrier {per('tma_late_n', uw)*ctas/ts:.0f}")
         print(f"   mma thread / tile-stage: wait A {st['mma_wait_a']/ts:.0f}  wait TMA {st['mma_wait_full']/ts:.0f}  wait acc {st['mma_wait_acc']/ts:.0f}  issue {st['mma_issue']/ts:.0f}  (total per CTA {st['mma_total']/ctas:.0f} cyc)")
+# the training variant of the kernel (straight-through arithmetic, loss numerators): which option costs what
+for name, kw in (("ste+sqerr", dict(want_sqerr=True, flags=L.FLAG_STE)), ("ste only", dict(flags=L.FLAG_STE)), ("sqerr only", dict(want_sqerr=True))):
+    t = timed(lambda: ops.encode(pk, x, 0, NQ, **kw), n=50)
+    print(f"train variant, {name}: {t:.3f} ms")
