@@ -39,6 +39,9 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "rvq_expire_codes": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _i, _vp]),
     "rvq_expire_stack": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _f, C.c_uint64, C.c_uint64,
                                _vp, _vp, _i, _vp]),
+    "rvq_bitpack_bytes": (_sz, [_i, _i, _i]),
+    "rvq_bitpack": (_i, [_vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "rvq_bitunpack": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _i64, _i64, _vp]),
     "rvq_kmeans_assign": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp]),
     "rvq_kmeans_update": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "rvq_residual_combine": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librvq_b200.so")
-SOURCES = ["rvq_abi.cu", "rvq_simt.cu", "rvq_tc.cu"]
+SOURCES = ["rvq_abi.cu", "rvq_simt.cu", "rvq_bits.cu", "rvq_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -131,6 +131,18 @@ int rvq_expire_stack(const void* pack, int K, int D,
                      const float* const* cluster_size_ptrs_host, float* const* embed_ptrs_host, float threshold,
                      uint64_t seed, uint64_t offset, int64_t* sel, int* fired, int flags, void* stream);
 
+/* ---- code bit-packing (the callers' side of the path: binary.BitPacker driven by compress.compress_to_file,
+ * binary.py:69-87 + compress.py:70-92, and binary.BitUnpacker, binary.py:104-121), one byte stream per batch item.
+ * Value number i = t*n_q + k (time-major, codebook-minor) occupies stream bits [i*bits, (i+1)*bits), little-endian in
+ * bits; a trailing partial byte is zero-padded.  codes: int64, element strides (sq, sb, st) for index [k, b, t] (the search's
+ * [n_q, B, T] output or the model's [B, K, T] view alike); values are masked to `bits` bits.  out / in: uint8, stream b at
+ * byte offset b * stride, rvq_bitpack_bytes(n_q, T, bits) bytes each.  1 <= bits <= 16, n_q <= 64 (pack).             */
+size_t rvq_bitpack_bytes(int n_q, int T, int bits);
+int rvq_bitpack(const int64_t* codes, int64_t sq, int64_t sb, int64_t st, int n_q, int B, int T, int bits,
+                unsigned char* out, int64_t out_stride, void* stream);
+int rvq_bitunpack(const unsigned char* in, int64_t in_stride, int n_q, int B, int T, int bits,
+                  int64_t* codes, int64_t sq, int64_t sb, int64_t st, void* stream);
+
 /* ---- k-means (core_vq.py:80-102) on flat fp32 samples [N, D] (contiguous).
  * assign: buckets[n] = argmin_k sum_d (x[n,d]-means[k,d])^2, lowest index on ties (:86-91);
  *         `pack` is an rvq_pack() image (n_q = 1) of the current means.

@@ -4,6 +4,6 @@ for v in $VARIANTS; do
   defs=${defs//,/ }; [ "$defs" = "-" ] && defs=""
   RVQ_TC_SRC="$src" RVQ_NVCC_DEFS="$defs" python -m encodec_pytorch_b200.build --force > gpurun_out/var_${name}_build.log 2>&1 || { echo "$name: build failed"; tail -5 gpurun_out/var_${name}_build.log; continue; }
   python scripts/diag_tc.py > gpurun_out/var_${name}.log 2>&1
-  echo "== $name [$defs]"; grep "n_q=32" gpurun_out/var_${name}.log
+  echo "== $name [$defs]"; grep "n_q=32\|train variant" gpurun_out/var_${name}.log
 done
 python -m encodec_pytorch_b200.build --force > /dev/null 2>&1
