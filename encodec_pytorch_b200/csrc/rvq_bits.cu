@@ -19,9 +19,16 @@ bitpack_kernel(const int64_t* __restrict__ codes, int64_t sq, int64_t sb, int64_
   extern __shared__ unsigned short vals[];                 // [kBT][K + 1]
   const int b = blockIdx.y, t0 = blockIdx.x * kBT, nt = min(kBT, T - t0), ld = K + 1;
   const unsigned mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
-  for (int idx = threadIdx.x; idx < K * kBT; idx += blockDim.x) {
-    const int k = idx / kBT, tt = idx - k * kBT;
-    if (tt < nt) vals[tt * ld + k] = (unsigned short)(unsigned(codes[int64_t(k) * sq + int64_t(b) * sb + int64_t(t0 + tt) * st]) & mask);
+  {
+    // thread = (time step, every other codebook): 128 consecutive time steps per codebook row are one coalesced kilobyte;
+    // eight independent loads in flight per thread
+    const int tt = threadIdx.x & (kBT - 1);
+    if (tt < nt) {
+      const int64_t* src = codes + int64_t(b) * sb + int64_t(t0 + tt) * st;
+      #pragma unroll 8
+      for (int k = threadIdx.x >> 7; k < K; k += kBitsThreads / kBT)
+        vals[tt * ld + k] = (unsigned short)(unsigned(__ldg(src + int64_t(k) * sq)) & mask);
+    }
   }
   __syncthreads();
   const int64_t nvals = int64_t(nt) * K, nbits = nvals * bits, nbytes = (nbits + 7) >> 3;

@@ -134,6 +134,25 @@ def segmented(name, b, t_total, seg, n_q, fr, bw, dev, reps, out):
     print(name, json.dumps(out[name]), flush=True)
 
 
+def bitpack(name, b, t, n_q, dev, reps, out):
+    """8(f)-1: the byte streams of binary.BitPacker for the codes of one encode (10 bits per code), and back."""
+    from encodec_pytorch_b200 import binary as BN
+    _, hbm_peak = peaks()
+    q = quantizer(n_q, dev).eval()
+    with torch.no_grad():
+        codes = q.encode(latents(b, t, 11, dev), 75, None)
+    frame = codes.transpose(0, 1)                        # [B, K, T] view of the search's [K, B, T] output (model.py:166)
+    ms_p = timed(lambda i: BN.pack_frame(frame, 10), reps)
+    packed = BN.pack_frame(frame, 10)
+    ms_u = timed(lambda i: BN.unpack_frame(packed, n_q, t, 10), reps)
+    vals = b * t * n_q
+    algo = vals * 8 + packed.numel()                     # int64 codes + packed bytes (either direction)
+    out[name] = {"shape_bkt": [b, n_q, t], "bits": 10, "values": vals, "packed_bytes": int(packed.numel()),
+                 "pack_ms": ms_p, "pack_hbm_gbs": algo / ms_p / 1e6, "unpack_ms": ms_u, "unpack_hbm_gbs": algo / ms_u / 1e6,
+                 "hbm_peak_gbs": hbm_peak}
+    print(name, json.dumps(out[name]), flush=True)
+
+
 def bulk(dev, out, full):
     """cfg5: frames/s and tensor fraction vs frame count."""
     tf_peak, _ = peaks()
@@ -178,6 +197,9 @@ def main():
     training("cfg3_training", 64, 750, 32, 75, 24.0, dev, max(3, reps // 3), out)
     encode_decode("cfg4_48khz_one_call", 32, 4500, 16, 150, 24.0, dev, reps, out)
     segmented("cfg4_48khz_31_segments", 32, 4500, 150, 16, 150, 24.0, dev, max(3, reps // 3), out)
+    bitpack("bitpack_cfg2_codes", 64, 750, 32, dev, reps, out)
+    bitpack("bitpack_cfg4_codes", 32, 4500, 16, dev, reps, out)
+    bitpack("bitpack_16M_codes", 512, 1000, 32, dev, reps, out)
     if not args.quick:
         bulk(dev, out, args.full)
     if args.out:
