@@ -235,6 +235,8 @@ def run_b200(args):
         ev_cmp = [torch.cuda.Event() for _ in range(nb)]
         ev_out = [torch.cuda.Event() for _ in range(nb)]
 
+        held = [None] * nb                                      # the codes of the last encode that used slot k
+
         def e2e_run(n_steps):
             for i in range(n_steps):
                 k = i % nb
@@ -245,13 +247,17 @@ def run_b200(args):
                     ev_in[k].record(s_in)
                 with torch.cuda.stream(s_cmp):
                     s_cmp.wait_event(ev_in[k])
+                    if i >= nb:
+                        s_cmp.wait_event(ev_out[k])             # the D2H copy that read held[k] is done: its memory may be reused
                     c = q.encode(xd[k], FRAME_RATE, BW)
                     ev_cmp[k].record(s_cmp)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[k])
                     ch[k].copy_(c, non_blocking=True)
-                    c.record_stream(s_out)
                     ev_out[k].record(s_out)
+                # keep the codes alive until slot k comes round again (ordered by ev_out above) instead of record_stream():
+                # the allocator then cycles through nb + 1 blocks and never falls back to cudaMalloc / event polling
+                held[k] = c
 
         e2e_run(2 * nb)
         barrier()
