@@ -489,25 +489,30 @@ using namespace rvq;
 // ------------------------------------------------------------------------------------------------
 // EMA apply / expiry / k-means update kernels
 // ------------------------------------------------------------------------------------------------
+// cluster_size <- decay*cluster_size + (1-decay)*bincount   (core_vq.py:227, :49-56); one block per stage
+__global__ void __launch_bounds__(1024)
+ema_cluster_kernel(MutPtrTable32 cs_tab, int stage_base, int K, const float* __restrict__ counts, float decay, float alpha) {
+  float* cs = cs_tab.p[blockIdx.x];
+  const float* cnt = counts + size_t(stage_base + blockIdx.x) * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) cs[k] = cs[k] * decay + alpha * cnt[k];
+}
+
+// embed_avg <- EMA; embed <- embed_avg / (laplace(cluster_size) * total)   (core_vq.py:229-235).  grid (stages, kEmaSplit):
+// every block re-derives the stage's total = sum(cluster_size) with the same 1024-thread reduction (so all blocks of a stage,
+// and the former one-block-per-stage kernel, agree bit for bit) and then takes its slice of the K*D elements.
+constexpr int kEmaSplit = 16;
 __global__ void __launch_bounds__(1024)
 ema_apply_kernel(MutPtrTable32 cs_tab, MutPtrTable32 ea_tab, MutPtrTable32 em_tab, int stage_base, int K, int D,
-                 const float* __restrict__ counts, const float* __restrict__ embed_sum,
-                 float decay, float alpha, float eps, float keps) {
+                 const float* __restrict__ embed_sum, float decay, float alpha, float eps, float keps) {
   __shared__ float red[32];
   __shared__ float s_total;
   const int s = blockIdx.x;
-  float* cs = cs_tab.p[s];
+  const float* cs = cs_tab.p[s];
   float* ea = ea_tab.p[s];
   float* em = em_tab.p[s];
-  const float* cnt = counts + size_t(stage_base + s) * K;
   const float* es = embed_sum + size_t(stage_base + s) * K * D;
-  // cluster_size <- decay*cluster_size + (1-decay)*bincount   (core_vq.py:227, :49-56)
   float part = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float v = cs[k] * decay + alpha * cnt[k];
-    cs[k] = v;
-    part += v;
-  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) part += cs[k];
   #pragma unroll
   for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
@@ -520,9 +525,10 @@ ema_apply_kernel(MutPtrTable32 cs_tab, MutPtrTable32 ea_tab, MutPtrTable32 em_ta
   }
   __syncthreads();
   const float total = s_total;
-  // embed_avg <- EMA; embed <- embed_avg / (laplace(cluster_size) * total)   (core_vq.py:229-235)
   const int n = K * D;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int per = (n + gridDim.y - 1) / gridDim.y;
+  const int i0 = blockIdx.y * per, i1 = min(n, i0 + per);
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     int k = i / D;
     float a = ea[i] * decay + alpha * es[i];
     ea[i] = a;
@@ -759,7 +765,9 @@ int rvq_ema_apply(float* const* cluster_size_ptrs_host, float* const* embed_avg_
       b.p[i] = i < ns ? embed_avg_ptrs_host[s0 + i] : nullptr;
       c.p[i] = i < ns ? embed_ptrs_host[s0 + i] : nullptr;
     }
-    ema_apply_kernel<<<ns, 1024, 0, st>>>(a, b, c, s0, K, D, counts, embed_sum, float(decay), alpha, float(epsilon), keps);
+    ema_cluster_kernel<<<ns, 1024, 0, st>>>(a, s0, K, counts, float(decay), alpha);
+    RVQ_LAUNCH_CHECK("ema_cluster_kernel");
+    ema_apply_kernel<<<dim3(ns, kEmaSplit), 1024, 0, st>>>(a, b, c, s0, K, D, embed_sum, float(decay), alpha, float(epsilon), keps);
     RVQ_LAUNCH_CHECK("ema_apply_kernel");
   }
   return RVQ_OK;
