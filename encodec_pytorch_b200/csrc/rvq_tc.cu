@@ -88,7 +88,8 @@ static_assert((Sm::m_size % 16) == 0 && (Sm::misc % 16) == 0, "alignment");
 #ifndef RVQ_TRACE_N0
 #define RVQ_TRACE_N0 2
 #endif
-constexpr int kTraceSteps = 6, kTraceEv = 16, kTraceN0 = RVQ_TRACE_N0;
+constexpr int kTraceSteps = 6, kTraceEv = 16;
+[[maybe_unused]] constexpr int kTraceN0 = RVQ_TRACE_N0;
 __device__ long long g_trace[2 * kTraceSteps * kTraceEv + 128 + 2 * 64];   // + per-chunk detail of the MMA thread / the producer for (slot 0, step 4)
 #ifdef RVQ_TC_TRACE
 #define RVQ_TRACE(X, n, ev, cond) do { if (blockIdx.x == 0 && (cond) && (n) >= kTraceN0 && (n) < kTraceN0 + kTraceSteps) { \
