@@ -46,7 +46,7 @@ __global__ void pack_copy_kernel(PtrTable32 src, unsigned char* pack, int stage_
 // plus slack (x1.125) for the tensor core's fp32 accumulation of 144 products
 constexpr float kMarginSlack = 1.0625f;              // fp32 accumulation of the 144 products, fp32 norm arithmetic
 constexpr float kHalfUlp     = 4.8828125e-4f;        // 2^-11: relative rounding error bound of fp16
-constexpr float kOutlierMul = 64.f;                  // codes with |c| > 64 * median are outliers
+constexpr float kOutlierMul = 64.f;                  // codes with |c| > 64 * (15/16-quantile of the norms) are outliers
 constexpr float kBigScore   = 60000.f;               // fp16-representable score of an outlier code
 constexpr float kHalfSafe   = 3.0e4f;                // |2c| elements and |c|^2 must stay below fp16 max
 
@@ -97,8 +97,11 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   __shared__ float s_thr, s_cref, s_cmin, s_outmin, s_cmax, s_db2;
   __shared__ int s_nout;
   if (threadIdx.x == 0) {
-    float med = norms[K / 2];
-    s_thr = kOutlierMul * med;
+    // reference norm for the outlier test: a high quantile (15/16), not the median -- a codebook whose norms are bimodal
+    // with the large group in the minority (e.g. the first EMA steps after a k-means init, where most rows have shrunk) must
+    // not have its large, winning codes classified as outliers (every frame would then take the exact scan)
+    const float ref = norms[K - 1 - K / 16];
+    s_thr = kOutlierMul * ref;
     s_cmin = norms[0];
     s_cmax = norms[K - 1];
     s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0; s_db2 = 0.f;

@@ -134,6 +134,36 @@ def segmented(name, b, t_total, seg, n_q, fr, bw, dev, reps, out):
     print(name, json.dumps(out[name]), flush=True)
 
 
+def trained_like(name, b, t, n_q, fr, bw, dev, reps, out, steps=25):
+    """codebooks fitted to the latents (k-means init on the first batch, then `steps` EMA training steps on
+    fresh batches) so that residual norms decay stage by stage as in a trained model; then the eval encode is timed."""
+    from encodec_pytorch_b200 import _ops as ops
+    tf_peak, _ = peaks()
+    q = quantizer(n_q, dev, kmeans=True).train()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.no_grad():
+            for i in range(steps):
+                q(latents(b, t, 500 + i, dev), fr, bw)
+    q.eval()
+    xs = [latents(b, t, 900 + i, dev) for i in range(6)]
+    with torch.no_grad():
+        ms = timed(lambda i: q.encode(xs[i % 6], fr, bw), reps)
+        codes = q.encode(xs[0], fr, bw)
+        st = ops.search_stats(q.vq._stack_pack())
+        r = xs[0]
+        norms = []
+        for i in (0, 1, 3, 7, 15, n_q - 1):
+            part = q.decode(codes[: i + 1])
+            norms.append(float((xs[0] - part).norm() / xs[0].norm()))
+    frames = b * t
+    out[name] = {"shape": [b, D, t], "n_q": n_q, "training_steps": steps, "encode_ms": ms,
+                 "encode_frames_per_s": frames / ms * 1e3, "encode_tensor_frac": frames / ms * 1e3 * n_q * FLOP / (tf_peak * 1e12),
+                 "certified_share": st["certified"] / max(1, st["searched"]), "rescored": st["rescored"], "fullscan": st["fullscan"],
+                 "relative_residual_norm_after_stage_1_2_4_8_16_last": norms}
+    print(name, json.dumps(out[name]), flush=True)
+
+
 def bitpack(name, b, t, n_q, dev, reps, out):
     """8(f)-1: the byte streams of binary.BitPacker for the codes of one encode (10 bits per code), and back."""
     from encodec_pytorch_b200 import binary as BN
@@ -197,6 +227,7 @@ def main():
     training("cfg3_training", 64, 750, 32, 75, 24.0, dev, max(3, reps // 3), out)
     encode_decode("cfg4_48khz_one_call", 32, 4500, 16, 150, 24.0, dev, reps, out)
     segmented("cfg4_48khz_31_segments", 32, 4500, 150, 16, 150, 24.0, dev, max(3, reps // 3), out)
+    trained_like("cfg2_trained_like", 64, 750, 32, 75, 24.0, dev, reps, out)
     bitpack("bitpack_cfg2_codes", 64, 750, 32, dev, reps, out)
     bitpack("bitpack_cfg4_codes", 32, 4500, 16, dev, reps, out)
     bitpack("bitpack_16M_codes", 512, 1000, 32, dev, reps, out)
