@@ -502,3 +502,31 @@ def test_training_forward_does_not_sync_the_host():
             finally:
                 torch.cuda.set_sync_debug_mode("default")
     assert r.codes.shape == (8, 4, 300) and torch.isfinite(r.penalty)
+
+
+def test_bimodal_codebook_norms_stay_on_the_tensor_path():
+    """Codebooks whose norms are bimodal with the large group in the minority (the first EMA steps after a k-means init:
+    most rows shrunk, the winning ones not) must not have their large codes classified as outliers -- every frame of the
+    stage would take the exact scan.  A genuinely exploding row (norm 3 000 against 10) still is one.  Codes are checked
+    stage-wise against the oracle either way."""
+    import encodec_pytorch_b200 as E
+    from encodec_pytorch_b200 import _ops as ops
+    torch.manual_seed(11)
+    n_q, K, D = 3, 1024, 128
+    q = E.ResidualVectorQuantizer(dimension=D, n_q=n_q, bins=K, kmeans_init=False).cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        e0 = torch.randn(K, D, generator=g)
+        e0[:900] *= 0.01                                     # 900 shrunk rows (norm ~0.1), 124 rows of norm ~11
+        q.vq.layers[0]._codebook.embed.copy_(e0.cuda())
+        e1 = torch.randn(K, D, generator=g) * 0.8
+        e1[7] *= 300.0                                       # one exploding row
+        q.vq.layers[1]._codebook.embed.copy_(e1.cuda())
+    q.vq.invalidate()
+    x = torch.randn(3, D, 333, generator=g)
+    pk = q.vq._stack_pack()
+    codes = ops.encode(pk, x.cuda(), 0, n_q)[0]
+    st = ops.search_stats(pk)
+    assert st["fullscan"] == 0, st                           # nobody fell back to the exact scan
+    chk = O.compare_codes_teacher_forced(module_states(q), x, codes.cpu())
+    assert chk["bad"] == 0 and chk["near_tie"] <= 5, chk
