@@ -669,6 +669,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
 #endif
     // load dims 64h..64h+63 of the latent tile `tile` into slot X: fp32 residual rows, |x|^2, fp16 operand in tensor
     // memory, rounding residue
+    // pull this warp's share of a tile (64 lines: one per dim, 32 consecutive frames x 4 B) into L2
+    auto prefetch_tile = [&](int tile) {
+      const int64_t n = int64_t(tile) * p.tf + f;
+      if (f < p.tf && n < p.N) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + lane) * p.fa.sxd));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + 32 + lane) * p.fa.sxd));
+      }
+    };
     auto load_tile = [&](int X, int tile) {
       float* rs = reinterpret_cast<float*>(smem + Sm::rs + X * kRsBytes);
       unsigned char* ms = smem + Sm::misc + X * Sm::m_size;
@@ -676,11 +684,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       const bool valid = f < p.tf && n < p.N;     // lanes beyond the tile's frames carry zeros and write nothing
       const int64_t xb = valid ? p.fa.base(n) : 0;
       float xsum = 0.f, e2 = 0.f;
-      // the warp's 64 lines (one per dim: 32 consecutive frames x 4 B) are asked for at once, then read 16 dims at a time
-      if (valid) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + lane) * p.fa.sxd));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + 32 + lane) * p.fa.sxd));
-      }
+      // the warp's 64 lines are asked for at once (a slot's later tiles were already requested a few stages before the end of
+      // the previous tile), then read 16 dims at a time
+      prefetch_tile(tile);
       #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         float v[16];
@@ -727,6 +733,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           RVQ_TICK(t_wait);
           RVQ_TRACE(X, n, 6, u == 0 && lane == 0);
           const bool last = s + 1 == p.n_q;
+          // a few stages before the tile ends: the slot's next tile starts its way from HBM to L2
+          if ((s + 4 == p.n_q || (p.n_q < 4 && s == 0)) && (jt + 1) * p.n_q < (X ? steps1 : steps0)) prefetch_tile(tile0 + X + 2 * (jt + 1));
           float sq = 0.f;
           // operand rows of this warp: TMEM lanes 32q + 16h .. +15, columns of slot X
           update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st),
