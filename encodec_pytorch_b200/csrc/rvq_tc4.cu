@@ -39,14 +39,22 @@
 
 #include <cstdlib>
 
+#ifndef RVQ_RING
+#define RVQ_RING 6
+#endif
+#ifndef RVQ_POOL_ITEMS
+#define RVQ_POOL_ITEMS 6
+#endif
+
 namespace rvq {
 
 namespace {
 
 constexpr int kM = 128;                 // frames per tile (UMMA M, TMEM lanes)
 constexpr int kN = kTcChunkCodes;       // 128 codes per MMA group (UMMA N)
-constexpr int kRing = 7;                // B ring slots; each holds one K-third of a chunk (6 K-groups = 3 K-steps)
+constexpr int kRing = RVQ_RING;                // B ring slots; each holds one K-third of a chunk (6 K-groups = 3 K-steps)
 constexpr int kSlotBytes = 6 * kTcLBO;  // 12288 B
+constexpr int kPoolItems = RVQ_POOL_ITEMS;   // listed frames whose candidate rows are staged in shared memory (4 rows of 512 B each)
 constexpr int kAccBufs = 3;             // accumulator buffers of kN TMEM columns
 constexpr int kTmemA = kAccBufs * kN;   // first TMEM column of the fp16 operands (64 columns per slot)
 constexpr int kThreadsTc = 16 * 32;
@@ -59,7 +67,10 @@ struct Sm {
   static constexpr uint32_t aug = 0;                               // [2 k-groups][128 rows][16 B], no swizzle
   static constexpr uint32_t ring = aug + 4096;
   static constexpr uint32_t rs = ring + kRing * kSlotBytes;        // 2 x fp32 [128 f][128 d], chunk-swizzled
-  static constexpr uint32_t misc = rs + 2 * kRsBytes;              // 2 x per-slot block (offsets m_*)
+  static constexpr uint32_t pool = rs + 2 * kRsBytes;              // fp32 [kPoolItems][4 candidates][128 d]: staged candidate rows
+  static constexpr uint32_t pcode = pool + kPoolItems * 2048;      // int4 [kPoolItems]: their codes
+  static constexpr uint32_t pnorm = pcode + kPoolItems * 16;       // float4 [kPoolItems]: their |c|^2
+  static constexpr uint32_t misc = pnorm + kPoolItems * 16;        // 2 x per-slot block (offsets m_*)
   static constexpr uint32_t m_cand = 0;                            // int4 [128]: candidate codes (-1 = none)
   static constexpr uint32_t m_ncnt = m_cand + kM * 16;             // int [128]
   static constexpr uint32_t m_cmask = m_ncnt + kM * 4;             // u32 [128] flagged classes   (a fresh tile: |x|^2 of dims 0..63)
@@ -374,9 +385,10 @@ template <bool TRAIN>
 __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsigned char* ms, int u, int lane, int s, int rot,
                                             int nchunks, int64_t tile_n0, const float* __restrict__ t32,
                                             const float* __restrict__ cn, uint32_t taddr, bool store, uint32_t bar_a, float& sq,
-                                            int trX, int trn, long long t_kernel0) {
+                                            const unsigned char* pool_g, uint32_t pool_s, int trX, int trn, long long t_kernel0) {
   const int q = u & 3, h = u >> 2;
   RVQ_TRACE3(trX, trn, u, 0);
+  int4* pcode = const_cast<int4*>(reinterpret_cast<const int4*>(pool_g + kPoolItems * 2048));
   const int* qc = reinterpret_cast<const int*>(ms + Sm::m_qcnt);
   const int nslow = qc[0], nwide = qc[1];
   const int4* cand = reinterpret_cast<const int4*>(ms + Sm::m_cand);
@@ -448,6 +460,69 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
       if (it.f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
     }
   };
+  // Listed frames 0 .. kPoolItems-1 of the queue: their (up to 4) candidate rows are asked for AHEAD of the winner rows, by
+  // async copies into the shared-memory pool (lane = 16-byte chunk; no registers are held while they fly), and settled
+  // below from shared memory.
+  const int npool = nslow < kPoolItems ? nslow : kPoolItems;
+  auto pool_request = [&](int i) {
+    const int f = slowq[i];
+    int4 cd = make_int4(-1, -1, -1, -1);
+    const uint32_t cmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
+    uint32_t bm2 = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + f * 4);
+    int w = 0;
+    while (bm2) {
+      const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
+      uint32_t cm2 = cmk;
+      while (cm2) {
+        const int code = code_of(a, __ffs(cm2) - 1, rot, nchunks); cm2 &= cm2 - 1;
+        if (w == 0) cd.x = code; else if (w == 1) cd.y = code; else if (w == 2) cd.z = code; else cd.w = code;
+        ++w;
+      }
+    }
+    const uint32_t dst = pool_s + uint32_t(i) * 2048u + uint32_t(lane) * 16u;
+    ptx::cp_async16(dst, reinterpret_cast<const float4*>(t32 + size_t(cd.x) * 128) + lane);
+    ptx::cp_async16(dst + 512, reinterpret_cast<const float4*>(t32 + size_t(cd.y) * 128) + lane);
+    if (cd.z >= 0) ptx::cp_async16(dst + 1024, reinterpret_cast<const float4*>(t32 + size_t(cd.z) * 128) + lane);
+    if (cd.w >= 0) ptx::cp_async16(dst + 1536, reinterpret_cast<const float4*>(t32 + size_t(cd.w) * 128) + lane);
+    if (lane == 0) pcode[i] = cd;
+    const int ck = lane == 0 ? cd.x : lane == 1 ? cd.y : lane == 2 ? cd.z : cd.w;
+    if (lane < 4 && ck >= 0) ptx::cp_async4(pool_s + uint32_t(kPoolItems) * 2064u + uint32_t(i) * 16u + uint32_t(lane) * 4u, cn + ck);
+  };
+  auto pool_settle = [&](int i) {
+    const int f = slowq[i];
+    const int4 cd = pcode[i];
+    const float4 pn = *reinterpret_cast<const float4*>(pool_g + kPoolItems * 2064 + i * 16);
+    const float4* rows = reinterpret_cast<const float4*>(pool_g + size_t(i) * 2048) + lane;
+    float* rp = rs + rs_off(f, lane);
+    const float4 rl = *reinterpret_cast<const float4*>(rp);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w0 = rows[0], w1 = rows[32], w2 = cd.z >= 0 ? rows[64] : z4, w3 = cd.w >= 0 ? rows[96] : z4;
+    float rr = dot4(rl, rl, 0.f), d0 = dot4(rl, w0, 0.f), d1 = dot4(rl, w1, 0.f), d2 = dot4(rl, w2, 0.f), d3 = dot4(rl, w3, 0.f);
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      rr += __shfl_xor_sync(0xffffffffu, rr, off);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
+    }
+    float best = inf_f(); int bcode = 0x7fffffff; float4 wsel = w0;       // NaN distances only: the first candidate
+    auto consider = [&](float d, float nrm, int code, const float4& w) {
+      const float e = (rr - 2.f * d) + nrm;
+      if (code >= 0 && (e < best || (e == best && code < bcode))) { best = e; bcode = code; wsel = w; }
+    };
+    consider(d0, pn.x, cd.x, w0); consider(d1, pn.y, cd.y, w1); consider(d2, pn.z, cd.z, w2); consider(d3, pn.w, cd.w, w3);
+    if (bcode == 0x7fffffff) bcode = cd.x;
+    *reinterpret_cast<float4*>(rp) = sub_row<TRAIN>(p, rl, wsel);
+    const int64_t nfr = tile_n0 + f;
+    if (lane == 0) {
+      *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;
+      if (f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
+    }
+  };
+  if (u < npool) {
+    #pragma unroll 1
+    for (int i = u; i < npool; i += kUpdWarps) pool_request(i);
+    ptx::cp_async_commit();
+  }
   Item it;
   float4 qa[8], qb[8];
   {
@@ -459,8 +534,15 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     for (int i = 0; i < 8; ++i) qb[i] = nB == 1 ? __ldg(rb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (nslow + nwide > 0) {
+    if (u < npool) {
+      ptx::cp_async_wait_all();
+      __syncwarp();
+      #pragma unroll 1
+      for (int i = u; i < npool; i += kUpdWarps) pool_settle(i);
+    }
+    // listed frames beyond the pool: rows through registers, one frame per warp at a time
     #pragma unroll 1
-    for (int i = u; i < nslow; i += kUpdWarps) { item_load(i, it); item_finish(it); }
+    for (int i = kPoolItems + u; i < nslow; i += kUpdWarps) { item_load(i, it); item_finish(it); }
     // wide candidate sets: one frame per warp at a time, handed out from the last warp down
     #pragma unroll 1
     for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
@@ -747,7 +829,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           float sq = 0.f;
           // operand rows of this warp: TMEM lanes 32q + 16h .. +15, columns of slot X
           update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st),
-                             tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, RVQ_BAR(a_ready, X), sq, X, n,
+                             tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, RVQ_BAR(a_ready, X), sq,
+                             smem + Sm::pool, sbase + Sm::pool, X, n,
 #ifdef RVQ_TC_TRACE
                              t_kernel0
 #else

@@ -1,0 +1,103 @@
+// Micro-benchmark: the winner-row gather of one tile-stage (128 random rows of 512 B out of an L2-resident 512 KB fp32
+// table) on every SM at once: (A) 16 x LDG.128 per thread of 8 warps into registers, (B) 128 bulk async copies (TMA 1-D,
+// 512 B each) into shared memory, completion on one mbarrier, (C) LDGSTS (cp.async 16 B per lane).  With and without a
+// concurrent TMA stream of a 295 KB codebook image per iteration (the search's B operand).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_gather ubench_gather.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "../encodec_pytorch_b200/csrc/rvq_ptx.cuh"
+using namespace rvq;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int kRows = 128, kIters = 200, kStream = 36864;
+__device__ __forceinline__ uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 10; }
+
+template <int MODE, bool STREAM>
+__global__ void __launch_bounds__(320, 1) gather_kernel(const float* tab, const unsigned char* image, long long* out, float* sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar_g, bar_s[2];
+  __shared__ int codes[kRows];
+  const uint32_t sbase = ptx::smem_u32(smem);     // [0, 64 KB) staging, [64 KB, 64 KB + 2 * 36 KB) stream ring
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { ptx::mbar_init(ptx::smem_u32(&bar_g), 1); ptx::mbar_init(ptx::smem_u32(&bar_s[0]), 1); ptx::mbar_init(ptx::smem_u32(&bar_s[1]), 1); ptx::fence_mbar_init(); }
+  uint32_t seed = blockIdx.x * 977u + 13u;
+  __syncthreads();
+  long long tsum = 0;
+  float acc = 0.f;
+  if (warp == 8 || warp == 9) {
+    // background stream: 8 chunks of 36 KB per iteration, double-buffered
+    if (STREAM && warp == 8 && lane == 0) {
+      uint32_t n = 0;
+      for (int it = 0; it < kIters * 8; ++it, ++n) {
+        const uint32_t b = ptx::smem_u32(&bar_s[n & 1]);
+        ptx::mbar_expect_tx(b, kStream);
+        ptx::bulk_g2s(sbase + 65536 + (n & 1) * kStream, image + size_t(it % 256) * kStream, kStream, b);
+        ptx::mbar_wait(b, (n >> 1) & 1);
+      }
+    }
+  } else {
+    for (int it = 0; it < kIters; ++it) {
+      if (MODE == 1 && threadIdx.x == 0) ptx::mbar_expect_tx(ptx::smem_u32(&bar_g), kRows * 512);
+      if (threadIdx.x < kRows) { uint32_t s2 = seed + threadIdx.x * 7919u + it * 104729u; codes[threadIdx.x] = lcg(s2) & 1023; }
+      asm volatile("bar.sync 1, 256;");
+      const long long t0 = clock64();
+      if (MODE == 0) {
+        const int g = lane >> 2, m = lane & 3;
+        const int fA = warp * 16 + g, fB = fA + 8;
+        const float4* ra = reinterpret_cast<const float4*>(tab + size_t(codes[fA]) * 128) + m;
+        const float4* rb = reinterpret_cast<const float4*>(tab + size_t(codes[fB]) * 128) + m;
+        float4 qa[8], qb[8];
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) qa[i] = __ldg(ra + 4 * i);
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) acc += qa[i].x + qb[i].y + qa[i].z + qb[i].w;
+      } else if (MODE == 1) {
+        if (lane < 16) {
+          const int f = warp * 16 + lane;
+          ptx::bulk_g2s(sbase + f * 512, tab + size_t(codes[f]) * 128, 512, ptx::smem_u32(&bar_g));
+        }
+        ptx::mbar_wait(ptx::smem_u32(&bar_g), it & 1);
+        acc += *reinterpret_cast<const float*>(smem + (threadIdx.x * 16) % 65536);
+      } else {
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int f = warp * 16 + i;
+          ptx::cp_async16(sbase + f * 512 + lane * 16, reinterpret_cast<const float4*>(tab + size_t(codes[f]) * 128) + lane);
+        }
+        ptx::cp_async_commit(); ptx::cp_async_wait_all();
+        acc += *reinterpret_cast<const float*>(smem + (threadIdx.x * 16) % 65536);
+      }
+      asm volatile("bar.sync 1, 256;");
+      tsum += clock64() - t0;
+    }
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = tsum / kIters;
+  if (acc == 123.456f) sink[0] = acc;
+}
+
+template <int MODE, bool STREAM> void run(const char* name, const float* tab, const unsigned char* img, long long* out, float* sink) {
+  const int smem = 65536 + 2 * kStream;
+  CK(cudaFuncSetAttribute(gather_kernel<MODE, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  gather_kernel<MODE, STREAM><<<148, 320, smem>>>(tab, img, out, sink);
+  CK(cudaDeviceSynchronize());
+  long long h[148]; CK(cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost));
+  long long mn = h[0], mx = h[0], sm = 0; for (int i = 0; i < 148; ++i) { mn = h[i] < mn ? h[i] : mn; mx = h[i] > mx ? h[i] : mx; sm += h[i]; }
+  printf("%-34s cycles per 64 KB gather: avg %lld  min %lld  max %lld  (%.1f B/clk/SM)\n", name, sm / 148, mn, mx, 65536.0 / (sm / 148.0));
+}
+int main() {
+  float* tab; unsigned char* img; long long* out; float* sink;
+  CK(cudaMalloc(&tab, 1024 * 128 * 4)); CK(cudaMalloc(&img, size_t(256) * kStream)); CK(cudaMalloc(&out, 148 * 8)); CK(cudaMalloc(&sink, 4));
+  CK(cudaMemset(tab, 0, 1024 * 128 * 4)); CK(cudaMemset(img, 0, size_t(256) * kStream));
+  for (int rep = 0; rep < 2; ++rep) {
+    run<0, false>("LDG.128 x16 (registers)", tab, img, out, sink);
+    run<1, false>("bulk 512 B x128 (TMA -> smem)", tab, img, out, sink);
+    run<2, false>("LDGSTS 16 B (cp.async -> smem)", tab, img, out, sink);
+    run<0, true>("LDG.128 x16 + codebook stream", tab, img, out, sink);
+    run<1, true>("bulk 512 B x128 + codebook stream", tab, img, out, sink);
+    run<2, true>("LDGSTS 16 B + codebook stream", tab, img, out, sink);
+  }
+  return 0;
+}
