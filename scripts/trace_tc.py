@@ -36,4 +36,4 @@ for c in range(8):
 for X in range(2):
     print(f"update warps, slot {X} step N0+2: start | resolve done | barrier passed | rows requested | frame A done | frame B done | operand stored")
     for u in range(8):
-        print(f"  warp {u}: " + "  ".join(str(arr[base + 128 + 64 * X + 8 * u + e]) for e in range(7)))
+        print(f"  warp {u}: " + "  ".join(str(arr[base + 128 + 64 * X + 8 * u + e]) for e in range(8)))
