@@ -245,12 +245,28 @@ def residual_combine(pk: CodebookPack, x: torch.Tensor, codes: torch.Tensor, sta
     return out
 
 
-def search_stats(pk: CodebookPack) -> tp.Dict[str, int]:
-    import ctypes as C
-    lib = L.load()
-    arr = (C.c_uint64 * 32)()
-    with _guard(pk.device):
-        L.check(lib.rvq_search_stats(pk.buf.data_ptr(), arr, L.stream_ptr(pk.device)), "rvq_search_stats")
-    names = ("searched", "certified", "rescored", "fullscan", "cyc_wait", "cyc_scores", "cyc_winner", "cyc_update",
-             "cyc_load", "cyc_total", "warps", "mma_wait_a", "mma_wait_full", "mma_wait_acc", "mma_total", "cyc_resolve", "cyc_pairbar", "tma_late_lat_sum", "tma_late_n", "mma_issue", "cand2", "cand3_4", "cand5_8", "cand9plus")
-    return {n: int(arr[i]) for i, n in enumerate(names)}
+class search_counters:
+    """Context manager: counts what the tcgen05 search does inside the block (``rvq_search_counters``).
+
+        with ops.search_counters(device) as c:
+            ops.encode(...)
+        c.read()  ->  {"searched", "certified", "rescored", "fullscan"}   (synchronises)
+
+    Off by default: the library writes no counters unless a buffer is registered for the calling thread."""
+
+    NAMES = ("searched", "certified", "rescored", "fullscan")
+
+    def __init__(self, device):
+        self.buf = torch.zeros(32, dtype=torch.int64, device=device)
+
+    def __enter__(self):
+        L.check(L.load().rvq_search_counters(self.buf.data_ptr()), "rvq_search_counters")
+        return self
+
+    def __exit__(self, *exc):
+        L.check(L.load().rvq_search_counters(None), "rvq_search_counters")
+        return False
+
+    def read(self) -> tp.Dict[str, int]:
+        vals = self.buf.cpu().tolist()
+        return {n: int(vals[i]) for i, n in enumerate(self.NAMES)}

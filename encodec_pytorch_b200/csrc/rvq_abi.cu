@@ -21,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   return RVQ_ECUDA;
 }
 
+static thread_local unsigned long long* g_counters = nullptr;
+unsigned long long* search_counters() { return g_counters; }
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // The library is built for sm_100a only: refuse anything else loudly (no fallback of any kind).
@@ -106,11 +109,8 @@ int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int6
 /* debug only (not part of the public header): timeline of CTA 0 of the last tcgen05 encode (RVQ_TC_TRACE builds) */
 int rvq_debug_trace(long long* out_host, int n) { cudaDeviceSynchronize(); return rvq::tc_debug_trace(out_host, n); }
 
-int rvq_search_stats(const void* pack, uint64_t* out_host, void* stream) {
-  if (int e = check_device()) return e;
-  RVQ_REQUIRE(pack && out_host, "rvq_search_stats: null pointer");
-  RVQ_CUDA(cudaMemcpyAsync(out_host, pack, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  RVQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+int rvq_search_counters(uint64_t* counters_dev) {
+  g_counters = reinterpret_cast<unsigned long long*>(counters_dev);
   return RVQ_OK;
 }
 

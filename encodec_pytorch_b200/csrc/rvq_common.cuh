@@ -13,7 +13,7 @@ namespace rvq {
 
 // ----------------------------------------------------------------------------------------------
 // Pack layout (device memory, caller-allocated, rvq_pack_bytes()):
-//   [0, 256)                 header: 4 x uint64 search counters (+ reserved)
+//   [0, 256)                 header (reserved; the pack is read-only after rvq_pack)
 //   per stage s (stride stage_bytes(K, D), 256-B aligned sections):
 //     tab32   fp32 [K][D]    row-major copy of embed             (gathers, exact re-score)
 //     tab32T  fp32 [D][K]    transposed copy                     (exact SIMT search tiles)
@@ -75,7 +75,6 @@ struct PackView {
   __host__ __device__ const float* cnorm(int s)  const { return (const float*)(stage(s) + L.off_cnorm); }
   __host__ __device__ const unsigned char* tc(int s) const { return stage(s) + L.off_tc; }
   __host__ __device__ const StageMeta* meta(int s) const { return (const StageMeta*)(stage(s) + L.off_meta); }
-  __host__ __device__ unsigned long long* counters() const { return (unsigned long long*)base; }
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -109,6 +108,16 @@ struct FrameAddr {
   int64_t sxb, sxd, sxt; int T;
   __device__ inline int64_t base(int64_t n) const { int64_t b = n / T; int64_t t = n - b * T; return b * sxb + t * sxt; }
 };
+
+// torch's CPU argmax (core_vq.py:188) propagates NaN: the first NaN distance wins; otherwise the smallest
+// distance, lowest index on ties.  (best, bcode) starts as (+inf, 0x7fffffff).
+__device__ __forceinline__ bool nan_aware_better(float dist, int code, float best, int bcode) {
+  if (dist != dist) return best == best || code < bcode;
+  return best == best && (dist < best || (dist == best && code < bcode));
+}
+
+// optional search counters of the calling thread (rvq_search_counters); nullptr = off
+unsigned long long* search_counters();
 
 // ---- entry points implemented per translation unit -------------------------------------------
 struct EncodeArgs {

@@ -187,9 +187,7 @@ int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* 
   RVQ_REQUIRE(meta_smem <= 200 * 1024, "rvq_pack: codebook_size %d too large", K);
   RVQ_CUDA(cudaFuncSetAttribute(pack_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta_smem));
   RVQ_CUDA(cudaMemsetAsync(pack, 0, kHeaderBytes, st));
-  // experiment knob (NOT rigorous below 1): scales the fp16 score-error margin to study its effect on the re-score rate
-  float margin_scale = 1.f;
-  if (const char* e = getenv("RVQ_MARGIN_SCALE")) margin_scale = (float)atof(e);
+  const float margin_scale = 1.f;
   for (int s0 = 0; s0 < n_q; s0 += 32) {
     int ns = n_q - s0 < 32 ? n_q - s0 : 32;
     PtrTable32 tab;
@@ -308,7 +306,7 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
           for (int i = 0; i < 4; ++i) {
             // core_vq.py:183-187: (|x|^2 - 2 x.e) + |e|^2, maximised after negation
             float dist = DIRECT ? acc[i][j] : (xx[ty * 4 + i] - 2.f * acc[i][j]) + cnj;
-            if (dist < bd[i]) { bd[i] = dist; bi[i] = code; }
+            if (nan_aware_better(dist, code, bd[i], bi[i])) { bd[i] = dist; bi[i] = code; }
           }
         }
       }
@@ -320,9 +318,9 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
       for (int off = 8; off > 0; off >>= 1) {
         float od = __shfl_xor_sync(0xffffffffu, bd[i], off);
         int oi = __shfl_xor_sync(0xffffffffu, bi[i], off);
-        if (od < bd[i] || (od == bd[i] && oi < bi[i])) { bd[i] = od; bi[i] = oi; }
+        if (oi != 0x7fffffff && nan_aware_better(od, oi, bd[i], bi[i])) { bd[i] = od; bi[i] = oi; }
       }
-      // NaN rows never satisfy '<': fall back to code 0 like an all-NaN argmax
+      // no code at all (K == 0 cannot happen): code 0
       if (tx == 0) win[ty * 4 + i] = bi[i] == 0x7fffffff ? 0 : bi[i];
     }
     __syncthreads();

@@ -37,8 +37,6 @@
 #include "rvq_common.cuh"
 #include "rvq_ptx.cuh"
 
-#include <cstdlib>
-
 namespace rvq {
 
 namespace {
@@ -189,13 +187,6 @@ __device__ __forceinline__ void pair_min(const uint32_t (&u)[16], const uint32_t
   #pragma unroll
   for (int j = 0; j < 16; ++j) cm16[j] = ptx::fmin3(cm16[j], __uint_as_float(u[j]), __uint_as_float(v[j]));
   bu = min16(u); bv = min16(v);
-}
-
-// torch's CPU argmax (core_vq.py:188) propagates NaN: the first NaN distance wins; otherwise the smallest
-// distance, lowest index on ties.  (best, bcode) starts as (+inf, 0x7fffffff).
-__device__ __forceinline__ bool nan_aware_better(float dist, int code, float best, int bcode) {
-  if (dist != dist) return best == best || code < bcode;
-  return best == best && (dist < best || (dist == best && code < bcode));
 }
 
 // Score-warp side.  Frames whose candidate set is the whole table (outside the fp16 image's validity range, NaN):
@@ -994,24 +985,16 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
     RVQ_CUDA(cudaFuncSetAttribute(tc_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::total));
     sm_dev = dev;
   }
-  PackView pv(a.pack, a.K, a.D);
-  RVQ_CUDA(cudaMemsetAsync(pv.counters(), 0, 32 * sizeof(unsigned long long), st));
   TcParams p;
   p.pack = (const unsigned char*)a.pack; p.K = a.K;
   p.x = a.x; p.fa = FrameAddr{a.sxb, a.sxd, a.sxt, a.T}; p.N = N;
   p.stage0 = a.stage0; p.n_q = a.n_q;
   p.codes = a.codes; p.residual_out = a.residual_out; p.sqerr = a.sqerr;
   p.ste = (a.flags & RVQ_FLAG_STE) ? 1 : 0;
-  p.counters = pv.counters();
-  // Two tiles are in flight per CTA, so every CTA should own an even number of tiles of equal size: with `passes`
-  // rounds of 2 tiles per CTA, a tile gets ceil(N / (2 * SMs * passes)) <= 128 frames (cfg2: 48 000 frames -> 2 rounds
-  // of 82-frame tiles instead of 2.5 tiles of 128 with one of them running alone).
-  const int64_t per_round = 2ll * sm_count * kM;
-  const int64_t passes = (N + per_round - 1) / per_round;
-  int64_t tf = (N + 2ll * sm_count * passes - 1) / (2ll * sm_count * passes);
-  tf = tf < 16 ? 16 : (tf > kM ? kM : tf);
-  tf = kM;   // measured on B200 (cfg2): full 128-frame tiles with a single-tile tail beat balanced 82-frame tiles (0.62 vs 0.67 ms)
-  if (const char* e = getenv("RVQ_TC_TILE_FRAMES")) { const int v = atoi(e); if (v >= 1 && v <= kM) tf = v; }   // tuning knob
+  p.counters = search_counters();     // nullptr unless the caller registered a buffer (rvq_search_counters)
+  // full 128-frame tiles: a CTA's odd last tile runs alone (measured on B200 at cfg2: 0.62 ms against 0.67 ms for balanced
+  // 82-frame tiles, whose MMAs cost the same as full ones)
+  const int64_t tf = kM;
   p.tf = int(tf);
   const int64_t ntiles = (N + tf - 1) / tf;
   // one tile per CTA while there are SMs to spare (a lone tile's stage is shorter than a pair's: small calls are latency-bound),

@@ -299,38 +299,29 @@ class VectorQuantization(nn.Module):
     def _plain(self) -> bool:
         return isinstance(self.project_in, nn.Identity) and isinstance(self.project_out, nn.Identity)
 
+    def _require_plain(self) -> None:
+        """The EnCodec models never project (model.py:260-264 builds ``dimension == codebook_dim``); the fused
+        kernels cover exactly that case and nothing routes around them."""
+        if not self._plain:
+            raise RuntimeError("projected codebooks (codebook_dim != dim) are not supported by the B200 RVQ path")
+
     def encode(self, x: torch.Tensor) -> torch.Tensor:
         """core_vq.py:289-293: ``[B, D, T]`` -> ``[B, T]`` int64."""
-        if self._plain:
-            L.require_cuda_f32(x, "x")
-            codes, _, _, _ = ops.encode(self._codebook._pack(), x, 0, 1)
-            return codes[0]
-        return self._codebook.encode(self.project_in(x.permute(0, 2, 1)))
+        self._require_plain()
+        L.require_cuda_f32(x, "x")
+        codes, _, _, _ = ops.encode(self._codebook._pack(), x, 0, 1)
+        return codes[0]
 
     def decode(self, embed_ind: torch.Tensor) -> torch.Tensor:
         """core_vq.py:295-299: ``[B, T]`` -> ``[B, D, T]`` (a permuted ``[B, T, D]`` buffer)."""
-        quantize = self._codebook.decode(embed_ind)
-        quantize = self.project_out(quantize)
-        return quantize.permute(0, 2, 1)
+        self._require_plain()
+        return self._codebook.decode(embed_ind).permute(0, 2, 1)
 
     def forward(self, x: torch.Tensor):
         """core_vq.py:301-324: returns ``(quantize [B, D, T], embed_ind [B, T], loss [1])``."""
-        if self._plain:
-            quantized, codes, losses = _stack_forward([self], x, 1, self.training)
-            return quantized, codes[0], losses[0]
-        # projected codebooks (never built by the EnCodec models): per-op path around the kernels
-        device = x.device
-        xp = self.project_in(x.permute(0, 2, 1))
-        quantize, embed_ind = self._codebook(xp)
-        if self.training:
-            quantize = xp + (quantize - xp).detach()
-        loss = torch.tensor([0.0], device=device, requires_grad=self.training)
-        if self.training:
-            _warn_issue25()
-            if self.commitment_weight > 0:
-                loss = loss + torch.nn.functional.mse_loss(quantize.detach(), xp) * self.commitment_weight
-        quantize = self.project_out(quantize).permute(0, 2, 1)
-        return quantize, embed_ind, loss
+        self._require_plain()
+        quantized, codes, losses = _stack_forward([self], x, 1, self.training)
+        return quantized, codes[0], losses[0]
 
 
 def _warn_issue25() -> None:
@@ -448,8 +439,9 @@ class ResidualVectorQuantization(nn.Module):
         self.layers = nn.ModuleList([VectorQuantization(**kwargs) for _ in range(num_quantizers)])
         self._pack_cache: tp.Optional[tp.Tuple[tp.Any, ops.CodebookPack]] = None
 
-    def _fusable(self, n: int) -> bool:
-        return all(l._plain for l in self.layers[:n])
+    def _require_plain(self, n: int) -> None:
+        for l in self.layers[:n]:
+            l._require_plain()
 
     def _stack_pack(self) -> ops.CodebookPack:
         """Search image of ALL stages (a prefix serves any ``n_q``), cached until a table changes."""
@@ -467,43 +459,21 @@ class ResidualVectorQuantization(nn.Module):
         """core_vq.py:337-355."""
         n_q = n_q or len(self.layers)
         n_q = min(n_q, len(self.layers))           # the reference's slice caps silently (:346)
-        if self._fusable(n_q):
-            return _stack_forward(self.layers, x, n_q, self.training, self._stack_pack)
-        quantized_out = 0.0
-        residual = x
-        all_losses, all_indices = [], []
-        for layer in self.layers[:n_q]:
-            quantized, indices, loss = layer(residual)
-            residual = residual - quantized.detach()
-            quantized_out = quantized_out + quantized
-            all_indices.append(indices)
-            all_losses.append(loss)
-        out_losses, out_indices = map(torch.stack, (all_losses, all_indices))
-        return quantized_out, out_indices, out_losses
+        self._require_plain(n_q)
+        return _stack_forward(self.layers, x, n_q, self.training, self._stack_pack)
 
     def encode(self, x: torch.Tensor, n_q: tp.Optional[int] = None) -> torch.Tensor:
         """core_vq.py:357-367: ``[B, D, T]`` fp32 -> ``[n_q, B, T]`` int64."""
         n_q = n_q or len(self.layers)
         n_q = min(n_q, len(self.layers))
-        if self._fusable(n_q):
-            L.require_cuda_f32(x, "x")
-            codes, _, _, _ = ops.encode(self._stack_pack(), x.detach(), 0, n_q)
-            return codes
-        residual = x
-        all_indices = []
-        for layer in self.layers[:n_q]:
-            indices = layer.encode(residual)
-            residual = residual - layer.decode(indices)
-            all_indices.append(indices)
-        return torch.stack(all_indices)
+        self._require_plain(n_q)
+        L.require_cuda_f32(x, "x")
+        codes, _, _, _ = ops.encode(self._stack_pack(), x.detach(), 0, n_q)
+        return codes
 
     def decode(self, q_indices: torch.Tensor) -> torch.Tensor:
         """core_vq.py:369-375: ``[n_q, B, T]`` int64 (any strides, any stage prefix) ->
         ``[B, D, T]`` fp32, stages summed in order."""
         n = int(q_indices.shape[0])
-        if self._fusable(n):
-            return ops.decode(self._stack_pack(), q_indices).permute(0, 2, 1)
-        quantized_out = torch.tensor(0.0, device=q_indices.device)
-        for i, indices in enumerate(q_indices):
-            quantized_out = quantized_out + self.layers[i].decode(indices)
-        return quantized_out
+        self._require_plain(n)
+        return ops.decode(self._stack_pack(), q_indices).permute(0, 2, 1)

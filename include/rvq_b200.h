@@ -161,13 +161,12 @@ int rvq_residual_combine(const void* pack, int K, int D,
                          int stage0, int n_q, const int64_t* codes, const float* w,
                          float* out, int flags, void* stream);
 
-/* ---- debug / evidence: counters of the tcgen05 search written by the last rvq_encode on
- * `stream`-ordered memory inside the pack.  out_host: 32 x uint64:
- *   [0] frame-stages searched, [1] certified unique, [2] re-scored candidates, [3] exact scans,
- *   [4..9] summed frame-warp cycles: waiting for scores, reading/min-reducing scores, choosing
- *   the winner, residual update, tile load, total; [10] frame warps counted.
- * Synchronises the stream.                                                                      */
-int rvq_search_stats(const void* pack, uint64_t* out_host, void* stream);
+/* ---- debug / evidence: optional counters of the tcgen05 search.  Registers, for the CALLING THREAD, a device buffer of
+ * 32 x uint64 that every later rvq_encode of this thread accumulates into (atomics on the encode's stream):
+ *   [0] frame-stages searched, [1] certified unique, [2] re-scored (candidate list / wide set), [3] exact scans.
+ * NULL (the default) turns the counters off; the codebook pack is never written after rvq_pack.  The caller zeroes
+ * and reads the buffer.                                                                               */
+int rvq_search_counters(uint64_t* counters_dev);
 
 #ifdef __cplusplus
 }

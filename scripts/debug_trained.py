@@ -22,8 +22,9 @@ with torch.no_grad():
         n = e.norm(dim=1)
         cs = l._codebook.cluster_size
         pki = ops.pack([e])
-        c, _, _, r = ops.encode(pki, res, 0, 1, want_residual=True)
-        st = ops.search_stats(pki)
+        with ops.search_counters(dev) as counters:
+            c, _, _, r = ops.encode(pki, res, 0, 1, want_residual=True)
+        st = counters.read()
         rn = res.permute(0, 2, 1).reshape(-1, 128).norm(dim=1)
         print(f"stage {i:2d}: code norms min {n.min():.4f} med {n.median():.4f} max {n.max():.4f}  max|e| {e.abs().max():.3f}  cluster_size min {cs.min():.3f} max {cs.max():.1f} | |r| med {rn.median():.3f} max {rn.max():.3f} | certified {st['certified']} rescored {st['rescored']} fullscan {st['fullscan']}")
         res = r.permute(0, 2, 1)

@@ -149,8 +149,9 @@ def trained_like(name, b, t, n_q, fr, bw, dev, reps, out, steps=25):
     xs = [latents(b, t, 900 + i, dev) for i in range(6)]
     with torch.no_grad():
         ms = timed(lambda i: q.encode(xs[i % 6], fr, bw), reps)
-        codes = q.encode(xs[0], fr, bw)
-        st = ops.search_stats(q.vq._stack_pack())
+        with ops.search_counters(dev) as counters:
+            codes = q.encode(xs[0], fr, bw)
+        st = counters.read()
         r = xs[0]
         norms = []
         for i in (0, 1, 3, 7, 15, n_q - 1):

@@ -123,13 +123,13 @@ def test_ties_wide_candidate_sets_and_non_finite_frames():
     assert torch.equal(got.cpu()[:, ~finite], want[:, ~finite])
     xf = x.clone()
     xf[2, :, 7] = 0.0; xf[2, :, 9] = 0.0; xf[2, :, 11] = 0.0
-    with torch.no_grad():
+    from encodec_pytorch_b200 import _ops as ops
+    with torch.no_grad(), ops.search_counters("cuda") as counters:
         gotf = q.encode(xf.cuda(), 75)
     assert torch.equal(gotf.cpu()[:, finite], got.cpu()[:, finite])      # frames are independent
     st = assert_codes_match(states, xf, gotf, O.rvq_encode(states, xf).numpy())
     assert (gotf[0, 0, :40] == 0).all() and (gotf[0, 1, :20] == 5).all()   # ties resolved to the lowest index
-    from encodec_pytorch_b200 import _ops as ops
-    stats = ops.search_stats(q.vq._stack_pack())
+    stats = counters.read()
     assert stats["searched"] >= case.b * case.t * case.n_q and stats["rescored"] > 60   # padded tile rows count too
 
 
@@ -525,8 +525,9 @@ def test_bimodal_codebook_norms_stay_on_the_tensor_path():
     q.vq.invalidate()
     x = torch.randn(3, D, 333, generator=g)
     pk = q.vq._stack_pack()
-    codes = ops.encode(pk, x.cuda(), 0, n_q)[0]
-    st = ops.search_stats(pk)
+    with ops.search_counters("cuda") as counters:
+        codes = ops.encode(pk, x.cuda(), 0, n_q)[0]
+    st = counters.read()
     assert st["fullscan"] == 0, st                           # nobody fell back to the exact scan
     chk = O.compare_codes_teacher_forced(module_states(q), x, codes.cpu())
     assert chk["bad"] == 0 and chk["near_tie"] <= 5, chk

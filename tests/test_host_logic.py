@@ -134,3 +134,18 @@ def test_product_package_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "rvq_oracle" not in src, f
+
+
+def test_projected_codebooks_raise_instead_of_falling_back():
+    """codebook_dim != dim is never built by the EnCodec models; the B200 path raises rather than run a per-op loop."""
+    import pytest
+    import torch
+    from encodec_pytorch_b200.quantization.core_vq import ResidualVectorQuantization, VectorQuantization
+    vq = VectorQuantization(dim=8, codebook_size=4, codebook_dim=4, kmeans_init=False)
+    for call in (lambda: vq.encode(torch.zeros(1, 8, 3)), lambda: vq.decode(torch.zeros(1, 3, dtype=torch.long)),
+                 lambda: vq(torch.zeros(1, 8, 3))):
+        with pytest.raises(RuntimeError, match="projected codebooks"):
+            call()
+    rvq = ResidualVectorQuantization(num_quantizers=2, dim=8, codebook_size=4, codebook_dim=4, kmeans_init=False)
+    with pytest.raises(RuntimeError, match="projected codebooks"):
+        rvq.encode(torch.zeros(1, 8, 3))
