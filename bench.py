@@ -29,10 +29,27 @@ METRIC = "rvq_encode_frames_per_s"
 UNIT = "frames/s"
 B, D, T, NQ, BINS, FRAME_RATE, BW = 64, 128, 750, 32, 1024, 75, 24.0
 FLOP_PER_FRAME_STAGE = 2 * BINS * D          # only the x.c^T contraction counts
-# dram__bytes_read.sum + dram__bytes_write.sum of one tc_encode_kernel launch at cfg2 (ncu --set full,
-# profiles/r1e_tc_encode_ncu_raw.csv): 51.22 MB + 1.83 MB; algorithmic: 24.6 MB latents + 12.3 MB codes (reads: + first touch of
-# the 43 MB pack, which then stays in L2; writes: the int64 codes mostly still sit dirty in the 126 MB L2 at kernel end)
-NCU_DRAM_BYTES_PER_LAUNCH = 53.05e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc_encode_kernel launch at cfg2, from the committed ncu --set full
+# capture named below (NOT measured by this run: ncu replays kernels, a bench run must not sit under it).  Algorithmic:
+# 24.6 MB latents + 12.3 MB codes; the capture also sees the first touch of the 43 MB pack, which then stays in L2.
+NCU_TRAFFIC_FILE = "profiles/r2a_tc_encode_ncu_raw.csv"
+
+
+def _ncu_traffic():
+    """(bytes per launch, source) read from the committed ncu capture; (None, reason) if it is missing."""
+    p = os.path.join(ROOT, NCU_TRAFFIC_FILE)
+    try:
+        import csv
+        rows = list(csv.reader(open(p)))
+        hdr, vals, units = rows[0], rows[2], rows[1]
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+            tot += float(vals[i].replace(",", "")) * scale
+        return tot, f"{NCU_TRAFFIC_FILE} (ncu --set full --clock-control none, one launch; constant of the capture, not of this run)"
+    except Exception as e:      # noqa: BLE001
+        return None, f"{NCU_TRAFFIC_FILE} unreadable: {e}"
 WORKLOAD = f"cfg2: 24 kHz 24 kbps RVQ encode, latents [{B},{D},{T}] fp32, n_q={NQ}, bins={BINS}"
 
 
@@ -112,55 +129,80 @@ def _physical_gpu_index(local: int) -> int:
 # --------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm restated in oracle/ (PyTorch-CPU ops in the reference's order)
 # --------------------------------------------------------------------------------------------
-def _cpu_encode_rate(batch_items: int, reps: int, budget_s: float):
+def _reference_module():
+    """The UNMODIFIED reference quantizer from the git-ignored baseline/_ref (scripts/install_reference.py), built under
+    torch.manual_seed(0) like our module, or None where it is not installed."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import install_reference as IR
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns = IR.import_reference()
+        torch.manual_seed(0)
+        return ns.quantization.ResidualVectorQuantizer(dimension=D, n_q=NQ, bins=BINS, kmeans_init=False).eval()
+    except Exception:           # noqa: BLE001
+        return None
+
+
+def _cpu_encoder():
+    """(callable x -> codes on the host cores, kind, description): the reference's own module when installed
+    (kind "reference"), else the oracle port of the same lines (kind "port")."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = _reference_module()
+    if ref is not None:
+        return (lambda x: ref.encode(x, FRAME_RATE, BW)), "reference", \
+            "unmodified reference ResidualVectorQuantizer.encode (baseline/_ref, vq.py:115-122 -> core_vq.py:357-367)"
     from oracle import cases as C
     from oracle import rvq_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
     states = C.codebooks(D, BINS, NQ, 0)
-    x = C.latents(batch_items, D, T, 1234)
+    return (lambda x: O.rvq_encode(states, x, NQ)), "port", "oracle port of core_vq.py:357-367"
+
+
+def _cpu_encode_rate(batch_items: int, reps: int, budget_s: float):
+    enc, kind, what = _cpu_encoder()
+    x = _latents(batch_items, D, T, 1234)
     with torch.no_grad():
-        O.rvq_encode(states, x[:1], NQ)                       # warm-up (thread pool, allocator)
+        enc(x[:1])                                            # warm-up (thread pool, allocator)
         times = []
         t_start = time.perf_counter()
         for _ in range(reps):
             t0 = time.perf_counter()
-            O.rvq_encode(states, x, NQ)
+            enc(x)
             times.append(time.perf_counter() - t0)
             if time.perf_counter() - t_start > budget_s:
                 break
     frames = batch_items * T
-    return frames / statistics.median(times), frames, len(times)
+    return frames / statistics.median(times), frames, len(times), kind, what
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cases as C
-    from oracle import rvq_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    states = C.codebooks(D, BINS, NQ, 0)
+    enc, kind, what = _cpu_encoder()
     # size the per-step sample so that a step costs ~0.15 s on this host
-    probe_rate, _, _ = _cpu_encode_rate(1, 2, 5.0)
+    probe_rate, _, _, _, _ = _cpu_encode_rate(1, 2, 5.0)
     items = max(1, min(B, int(round(probe_rate * 0.15 / T))))
-    x = C.latents(items, D, T, 1234)
+    x = _latents(items, D, T, 1234)
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 3))):
-            O.rvq_encode(states, x, NQ)
+            enc(x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.rvq_encode(states, x, NQ)
+            enc(x)
         dt = time.perf_counter() - t0
     frames = items * T
     value = frames * args.steps / dt
-    sample = f"{items} of {B} batch items ({frames} frames, n_q={NQ}) per step, oracle port of core_vq.py:357-367"
+    sample = f"{items} of {B} batch items ({frames} frames, n_q={NQ}) per step, {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -171,6 +213,58 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
+def _timed(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def _extras(q, dev, xs, frames, peaks):
+    """Secondary blocks of the N=1 line: (1) `trained_like`: the same encode on codebooks FITTED to the latents (k-means init
+    + 25 EMA training forwards) -- real EnCodec tables are fitted, and fitted tables put more frame-stages
+    on the exact re-score path; (2) `gpu_eager_reference`: the unmodified reference module moved to the same GPU and run
+    eagerly in fp32 on the same tensors -- the "existing GPU path" (SURVEY.md 8(d)); (3) the training forward."""
+    import warnings
+    import encodec_pytorch_b200 as E
+    from encodec_pytorch_b200 import _ops as ops
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(0)
+        qt = E.ResidualVectorQuantizer(dimension=D, n_q=NQ, bins=BINS, kmeans_init=True, kmeans_iters=10).to(dev).train()
+        for i in range(26):
+            qt(xs[i % len(xs)], FRAME_RATE, BW)
+        t_train = _timed(lambda: qt(xs[3], FRAME_RATE, BW), 20)
+        qt.eval()
+        with ops.search_counters(dev) as counters:
+            qt.encode(xs[0], FRAME_RATE, BW)
+        st = counters.read()
+        ms = _timed(lambda: qt.encode(xs[1], FRAME_RATE, BW), 50)
+    ach = frames * NQ * FLOP_PER_FRAME_STAGE / (ms * 1e-3) / 1e12
+    out["trained_like"] = {"ms": ms, "frames_per_s": frames / (ms * 1e-3), "achieved": ach, "frac": ach / peaks["tflops"],
+                           "certified_share": st["certified"] / max(1, st["searched"]), "rescored": st["rescored"],
+                           "fullscan": st["fullscan"], "fit": "k-means init (10 iterations) + 25 EMA training forwards on the bench latents"}
+    out["train_forward"] = {"ms": t_train, "frames_per_s": frames / (t_train * 1e-3),
+                            "what": "steady-state training forward (search, quantized sum, commitment losses, expiry, EMA update)"}
+    ref = _reference_module()
+    if ref is not None:
+        ref = ref.to(dev)
+        with torch.no_grad():
+            ms_ref = _timed(lambda: ref.encode(xs[0], FRAME_RATE, BW), 5, warm=2)
+            same = float((ref.encode(xs[0], FRAME_RATE, BW) == q.encode(xs[0], FRAME_RATE, BW)).float().mean())
+        out["gpu_eager_reference"] = {"ms": ms_ref, "frames_per_s": frames / (ms_ref * 1e-3),
+                                      "codes_equal_share": same,
+                                      "what": "unmodified reference ResidualVectorQuantizer.encode (baseline/_ref) on the same B200, eager fp32"}
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     import encodec_pytorch_b200 as E
@@ -223,12 +317,17 @@ def run_b200(args):
         total_ms = t_start.elapsed_time(t_end)
         kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
 
-        # ---- end to end: pinned host latents in, int64 codes back to pinned host, every step.  The three legs of a step
-        # (H2D copy, encode through the public API, D2H copy) run on three streams with 3-deep buffers, the way a serving
-        # loop would drive the module: a step's copies overlap its neighbours' kernels, nothing is skipped or cached. -----
+        # ---- end to end: pinned host latents in, the codes back to pinned host in the reference's own wire format (the
+        # `.ecdc` payload: 10 bits per code, time-major / codebook-minor, binary.py:55-88 -- what compress.py:64-92 writes),
+        # every step.  The legs of a step (H2D copy, encode + bit-packing through the public API, D2H copy) run on three
+        # streams with 3-deep buffers, the way a serving loop would drive the module: a step's copies overlap its
+        # neighbours' kernels, nothing is skipped or cached.  (int64 codes would be 6.4x the bytes for the same 10 bits.) -----
+        from encodec_pytorch_b200 import binary as BN
         nb = 3
+        bits = 10
+        pk_bytes = BN.packed_nbytes(NQ, T, bits)
         xh = [_latents(B, D, T, 99 + i).pin_memory() for i in range(nb)]
-        ch = [torch.empty((NQ, B, T), dtype=torch.int64).pin_memory() for _ in range(nb)]
+        ch = [torch.empty((B, pk_bytes), dtype=torch.uint8).pin_memory() for _ in range(nb)]
         xd = [torch.empty_like(xs[0]) for _ in range(nb)]
         s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         ev_in = [torch.cuda.Event() for _ in range(nb)]
@@ -249,7 +348,7 @@ def run_b200(args):
                     s_cmp.wait_event(ev_in[k])
                     if i >= nb:
                         s_cmp.wait_event(ev_out[k])             # the D2H copy that read held[k] is done: its memory may be reused
-                    c = q.encode(xd[k], FRAME_RATE, BW)
+                    c = BN.pack_frame(q.encode(xd[k], FRAME_RATE, BW).transpose(0, 1), bits)   # [B, K, T] view, model.py:166
                     ev_cmp[k].record(s_cmp)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[k])
@@ -269,6 +368,24 @@ def run_b200(args):
         e_end.record(s_out)
         barrier()
         e2e_ms = e_start.elapsed_time(e_end)
+        # the packed bytes are the encode's codes: unpack the last slot on the host side of the check
+        torch.cuda.synchronize()
+        k_last = (args.steps - 1) % nb
+        chk = BN.unpack_frame(ch[k_last].to(dev), NQ, T, bits)
+        assert torch.equal(chk, q.encode(xh[k_last].to(dev), FRAME_RATE, BW).transpose(0, 1)), "e2e payload does not decode to the codes"
+
+        # ---- sustained: the same step back to back for >= 2 s (clocks settle under load; compare with the sustained peak) ----
+        n_sus = max(args.steps, int(2.2 / max(1e-6, total_ms / args.steps * 1e-3)))
+        sampler2 = ClockSampler(_physical_gpu_index(local))
+        sampler2.start()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for i in range(n_sus):
+            q.encode(xs[i % n_sets], FRAME_RATE, BW)
+        u1.record()
+        barrier()
+        sus_ms = u0.elapsed_time(u1)
+        clocks_sus = sampler2.stop()
 
         # ---- secondary: decode (HBM/L2-bound gather) ---------------------------------------------
         codes = q.encode(xs[0], FRAME_RATE, BW)
@@ -283,6 +400,10 @@ def run_b200(args):
         torch.cuda.synchronize()
         dec_ms = d0.elapsed_time(d1) / 20
 
+        extras = {}
+        if world == 1 and not args.quick:
+            extras = _extras(q, dev, xs, frames, peaks)
+
     times = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -292,7 +413,9 @@ def run_b200(args):
 
     if rank == 0:
         achieved = frames * NQ * FLOP_PER_FRAME_STAGE / (kernel_ms * 1e-3) / 1e12
-        cpu_rate, cpu_frames, cpu_reps = _cpu_encode_rate(8, 5, 20.0) if world == 1 else (None, 0, 0)
+        cpu_rate, cpu_frames, cpu_reps, cpu_kind, cpu_what = _cpu_encode_rate(8, 5, 20.0) if world == 1 else (None, 0, 0, "", "")
+        traffic, traffic_src = _ncu_traffic()
+        sus_achieved = frames * NQ * FLOP_PER_FRAME_STAGE * n_sus / (sus_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -303,22 +426,31 @@ def run_b200(args):
                        "codebooks": "kaiming-uniform, torch.manual_seed(0) (reference constructor)",
                        "parallelism": f"frames sharded over {world} rank(s), no data-path collective"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "fused n_q-stage encode (one launch per step)", "kernel_ms": kernel_ms,
                          "peak_source": peaks["source"] + " burst (kernel timed alone)",
                          "frac_of_sustained": (achieved / peaks["tflops_sustained"]) if peaks["tflops_sustained"] else None},
+            "sustained": {"seconds": sus_ms * 1e-3, "steps": n_sus, "frames_per_s": frames * n_sus / (sus_ms * 1e-3),
+                          "achieved": sus_achieved, "peak": peaks["tflops_sustained"] or None, "unit": "TFLOP/s",
+                          "frac": (sus_achieved / peaks["tflops_sustained"]) if peaks["tflops_sustained"] else None,
+                          "frac_of_burst_peak": sus_achieved / peaks["tflops"], "clocks": clocks_sus,
+                          "scope": "this rank" if world > 1 else "the job"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * T * 4,
-                    "d2h_bytes_per_step": NQ * B * T * 8, "ms_per_step": e2e_ms / args.steps,
-                    "how": "public API (ResidualVectorQuantizer.encode) on 3 streams: H2D / encode / D2H of neighbouring steps overlap"},
+                    "d2h_bytes_per_step": B * pk_bytes, "ms_per_step": e2e_ms / args.steps,
+                    "how": "public API on 3 streams (H2D / encode + pack / D2H of neighbouring steps overlap): pinned fp32 latents in, "
+                           "ResidualVectorQuantizer.encode -> binary.pack_frame, the codes out as the reference's .ecdc payload "
+                           f"({bits} bits per code, binary.py:55-88; {B * pk_bytes} B instead of {NQ * B * T * 8} B of int64), "
+                           "checked to unpack to the encode's codes"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "decode": {"frames_per_s": frames / (dec_ms * 1e-3), "ms": dec_ms,
                        "hbm_gbs": frames * (8 * NQ + 4 * D) / (dec_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]},
         }
         if cpu_rate is not None:
-            line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_kind,
                                     "sample": f"8 of {B} batch items ({cpu_frames} frames, n_q={NQ}), median of {cpu_reps} "
-                                              "runs of the oracle port of core_vq.py:357-367"}
+                                              f"runs of the {cpu_what}"}
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -330,6 +462,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="skip the secondary blocks (trained-like stack, eager GPU reference)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

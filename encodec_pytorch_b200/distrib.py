@@ -15,6 +15,25 @@ import torch
 import torch.distributed as dist
 
 
+# Cross-rank synchronisation of the codebook buffers in training.  OFF by default: the reference runs DDP with
+# ``broadcast_buffers=False`` and left both call sites commented out (core_vq.py:157, :175), so every rank keeps its own
+# EMA statistics -- a drop-in must not add blocking collectives (or change checkpoints) behind the caller's back.
+# ``sync_buffers(True)`` turns on what BASELINE.json's north_star describes: one all-reduce of the packed EMA statistics
+# per training forward and a rank-0 broadcast after k-means init, so that N ranks on N frame shards equal one rank on the
+# whole batch.  Every rank must then run the same sequence of training forwards.
+_SYNC = {"enabled": False, "group": None}
+
+
+def sync_buffers(enabled: bool = True, group=None) -> None:
+    """Enable / disable the EMA all-reduce and the k-means-init broadcast (process-wide switch)."""
+    _SYNC["enabled"] = bool(enabled)
+    _SYNC["group"] = group
+
+
+def sync_enabled() -> bool:
+    return _SYNC["enabled"] and is_distributed()
+
+
 def rank() -> int:
     """distrib.py:14-18."""
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
@@ -33,7 +52,7 @@ def is_distributed() -> bool:
 def all_reduce(tensor: torch.Tensor, op=None):
     """distrib.py:32-34: in-place SUM over ranks; no-op in a single process."""
     if is_distributed():
-        return dist.all_reduce(tensor, dist.ReduceOp.SUM if op is None else op)
+        return dist.all_reduce(tensor, dist.ReduceOp.SUM if op is None else op, group=_SYNC["group"])
     return None
 
 
@@ -48,13 +67,15 @@ def _check_count(tensors: tp.List[torch.Tensor]) -> None:
                            "at least one worker has a different one.")
 
 
-def broadcast_tensors(tensors: tp.Iterable[torch.Tensor], src: int = 0) -> None:
-    """distrib.py:55-68: broadcast the floating-point tensors from ``src`` (async, then wait)."""
+def broadcast_tensors(tensors: tp.Iterable[torch.Tensor], src: int = 0, check: bool = True) -> None:
+    """distrib.py:55-68: broadcast the floating-point tensors from ``src`` (async, then wait).  ``check=False`` skips the
+    count check (an all-reduce + host read) where the list is structurally the same on every rank."""
     if not is_distributed():
         return
     floats = [t for t in tensors if torch.is_floating_point(t) or torch.is_complex(t)]
-    _check_count(floats)
-    handles = [dist.broadcast(t.data, src=src, async_op=True) for t in floats]
+    if check:
+        _check_count(floats)
+    handles = [dist.broadcast(t.data, src=src, async_op=True, group=_SYNC["group"]) for t in floats]
     for h in handles:
         h.wait()
 

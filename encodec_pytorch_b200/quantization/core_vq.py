@@ -146,8 +146,8 @@ class EuclideanCodebook(nn.Module):
     # ---- reference API ------------------------------------------------------------------------
     @torch.jit.ignore
     def init_embed_(self, data: torch.Tensor) -> None:
-        """core_vq.py:146-157: k-means on the first batch; then (the step the reference left as a
-        FIXME) broadcast the initialised buffers from rank 0 so all ranks start in sync."""
+        """core_vq.py:146-157: k-means on the first batch; with ``distrib.sync_buffers(True)`` also the step the
+        reference left as a FIXME: broadcast the initialised buffers from rank 0 so all ranks start in sync."""
         if self._is_inited():
             return
         L.require_cuda_f32(data, "init_embed_ data")
@@ -158,7 +158,8 @@ class EuclideanCodebook(nn.Module):
             self.embed_avg.data.copy_(embed.clone())
             self.cluster_size.data.copy_(cluster_size)
             self.inited.data.copy_(torch.Tensor([True]))
-            distrib.broadcast_tensors(self.buffers())
+            if distrib.sync_enabled():             # opt-in (distrib.sync_buffers): all ranks start from rank 0's tables
+                distrib.broadcast_tensors(self.buffers(), check=False)
         self._inited_host = True
         self._tables_changed()
 
@@ -233,11 +234,12 @@ class EuclideanCodebook(nn.Module):
 def _update_stack(codebooks: tp.Sequence[EuclideanCodebook], pk: ops.CodebookPack, x_bdt: torch.Tensor,
                   codes: torch.Tensor, stage0: int, flags: int) -> None:
     """EMA update of core_vq.py:227-235 for a run of stages at once: bincount + per-code residual
-    sums (``rvq_ema_stats``), ONE all-reduce of the packed statistics across the frame shards
-    (the role of distrib.all_reduce, distrib.py:32-34), then EMA / Laplace smoothing / table
-    overwrite in place (``rvq_ema_apply``)."""
+    sums (``rvq_ema_stats``), with ``distrib.sync_buffers(True)`` ONE all-reduce of the packed statistics
+    across the frame shards (the role of distrib.all_reduce, distrib.py:32-34), then EMA / Laplace smoothing /
+    table overwrite in place (``rvq_ema_apply``)."""
     flat, counts, esum = ops.ema_stats(pk, x_bdt, codes, stage0, flags)
-    distrib.all_reduce_stats(flat)
+    if distrib.sync_enabled():                     # opt-in (distrib.sync_buffers): statistics of the global batch
+        distrib.all_reduce_stats(flat)
     cb0 = codebooks[0]
     ops.ema_apply([cb.cluster_size for cb in codebooks], [cb.embed_avg for cb in codebooks],
                   [cb.embed for cb in codebooks], counts, esum, cb0.decay, cb0.epsilon)

@@ -44,6 +44,7 @@ ref = {k: v.clone() for k, v in q_ref.state_dict().items()}
 # 2. the sharded job
 dist.init_process_group("nccl", device_id=dev)
 assert distrib.world_size() == world
+distrib.sync_buffers(True)        # opt-in: EMA all-reduce + k-means broadcast (default off, like the reference)
 q_sh, codes_sh = run(lambda b: distrib.shard_frames(b))
 lo, hi = distrib.shard_frames(B)
 worst = {}
