@@ -126,6 +126,29 @@ def _physical_gpu_index(local: int) -> int:
     return local
 
 
+def _bind_near_gpu(local: int):
+    """Pin this rank's threads (and with them the first touch of its pinned buffers) to the CPUs NVML reports as local to
+    its GPU, so that N ranks do not all stage their copies through one NUMA node.  Best effort; returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(_physical_gpu_index(local))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:       # noqa: BLE001
+            node = None
+        return {"cpus": f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else None, "allowed": len(allowed), "numa_node": node}
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:80]}
+
+
 # --------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm restated in oracle/ (PyTorch-CPU ops in the reference's order)
 # --------------------------------------------------------------------------------------------
@@ -276,6 +299,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    binding = _bind_near_gpu(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of stdout: one JSON line only
@@ -442,6 +466,7 @@ def run_b200(args):
                            f"({bits} bits per code, binary.py:55-88; {B * pk_bytes} B instead of {NQ * B * T * 8} B of int64), "
                            "checked to unpack to the encode's codes"},
             "gpu_launches": int(launches),
+            "host_binding": binding,
             "clocks": clocks,
             "decode": {"frames_per_s": frames / (dec_ms * 1e-3), "ms": dec_ms,
                        "hbm_gbs": frames * (8 * NQ + 4 * D) / (dec_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]},

@@ -18,6 +18,8 @@ FLAG_STE = 1
 FLAG_FORCE_EXACT = 2
 FLAG_DIRECT_DIST = 4
 FLAG_ACCUM_Q = 8
+FLAG_CODES_BKT = 16
+FLAG_OUT_BDT = 32
 
 _lib: tp.Optional[C.CDLL] = None
 
@@ -33,6 +35,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "rvq_pack": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
     "rvq_encode": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "rvq_decode": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _vp]),
+    "rvq_decode_ex": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp]),
     "rvq_ema_stats": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "rvq_ema_apply": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _dbl, _dbl, _vp]),
     "rvq_expire_replace": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),

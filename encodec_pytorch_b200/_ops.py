@@ -57,11 +57,13 @@ def _strides_bdt(x: torch.Tensor) -> tp.Tuple[int, int, int]:
 
 def encode(pk: CodebookPack, x: torch.Tensor, stage0: int, n_q: int, *,
            want_quantized: bool = False, want_sqerr: bool = False, want_residual: bool = False,
-           quantized_accum: tp.Optional[torch.Tensor] = None, flags: int = 0):
+           quantized_accum: tp.Optional[torch.Tensor] = None, flags: int = 0,
+           codes_bkt: bool = False, out_bdt: bool = False):
     """Fused multi-stage search on ``x [B, D, T]`` (any strides).
 
     Returns ``(codes [n_q,B,T] int64, quantized [B,T,D] | None, sqerr [n_q] float64 | None,
-    residual [B,T,D] | None)``."""
+    residual [B,T,D] | None)``.  ``codes_bkt``: the codes come as a contiguous ``[B, n_q, T]`` tensor (model.py:166's
+    layout) instead; ``out_bdt``: ``quantized`` comes as a contiguous ``[B, D, T]`` tensor."""
     lib = L.load()
     L.require_cuda_f32(x, "x")
     if x.dim() != 3 or x.shape[1] != pk.D:
@@ -70,14 +72,19 @@ def encode(pk: CodebookPack, x: torch.Tensor, stage0: int, n_q: int, *,
         raise RuntimeError("stage range outside the codebook pack")
     B, D, T = (int(v) for v in x.shape)
     dev = x.device
-    codes = torch.empty((n_q, B, T), dtype=torch.int64, device=dev)
+    if codes_bkt:
+        flags |= L.FLAG_CODES_BKT
+    if out_bdt:
+        flags |= L.FLAG_OUT_BDT
+    codes = torch.empty((B, n_q, T) if codes_bkt else (n_q, B, T), dtype=torch.int64, device=dev)
+    qshape = (B, D, T) if out_bdt else (B, T, D)
     quantized = None
     if quantized_accum is not None:
         quantized = quantized_accum
         flags |= L.FLAG_ACCUM_Q
-        assert quantized.is_contiguous() and tuple(quantized.shape) == (B, T, D)
+        assert quantized.is_contiguous() and tuple(quantized.shape) == qshape
     elif want_quantized:
-        quantized = torch.empty((B, T, D), dtype=torch.float32, device=dev)
+        quantized = torch.empty(qshape, dtype=torch.float32, device=dev)
     sqerr = torch.zeros(n_q, dtype=torch.float64, device=dev) if want_sqerr else None
     residual = torch.empty((B, T, D), dtype=torch.float32, device=dev) if want_residual else None
     sb, sd, st = _strides_bdt(x)
@@ -88,8 +95,9 @@ def encode(pk: CodebookPack, x: torch.Tensor, stage0: int, n_q: int, *,
     return codes, quantized, sqerr, residual
 
 
-def decode(pk: CodebookPack, codes: torch.Tensor) -> torch.Tensor:
-    """``codes [n_q, B, T]`` int64 (any strides) -> ``[B, T, D]`` fp32 (stage-ordered sum)."""
+def decode(pk: CodebookPack, codes: torch.Tensor, out_bdt: bool = False) -> torch.Tensor:
+    """``codes [n_q, B, T]`` int64 (any strides) -> ``[B, T, D]`` fp32 (stage-ordered sum); a contiguous ``[B, D, T]``
+    tensor with ``out_bdt``."""
     lib = L.load()
     if not codes.is_cuda:
         raise RuntimeError("decode: expected CUDA codes; the B200 RVQ path has no CPU fallback")
@@ -100,11 +108,11 @@ def decode(pk: CodebookPack, codes: torch.Tensor) -> torch.Tensor:
     n_q, B, T = (int(v) for v in codes.shape)
     if n_q > pk.n_q:
         raise RuntimeError(f"codes carry {n_q} stages, the stack has {pk.n_q}")
-    out = torch.empty((B, T, pk.D), dtype=torch.float32, device=codes.device)
+    out = torch.empty((B, pk.D, T) if out_bdt else (B, T, pk.D), dtype=torch.float32, device=codes.device)
     sq, sb, st = (int(v) for v in codes.stride())
     with _guard(codes.device):
-        L.check(lib.rvq_decode(pk.buf.data_ptr(), pk.K, pk.D, codes.data_ptr(), sq, sb, st, n_q, B, T,
-                               out.data_ptr(), L.stream_ptr(codes.device)), "rvq_decode")
+        L.check(lib.rvq_decode_ex(pk.buf.data_ptr(), pk.K, pk.D, codes.data_ptr(), sq, sb, st, n_q, B, T,
+                                  out.data_ptr(), L.FLAG_OUT_BDT if out_bdt else 0, L.stream_ptr(codes.device)), "rvq_decode_ex")
     return out
 
 

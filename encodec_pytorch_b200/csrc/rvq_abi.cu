@@ -91,7 +91,7 @@ int rvq_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int6
   RVQ_REQUIRE(int64_t(B) * T < (int64_t(1) << 31), "rvq_encode: more than 2^31 frames in one call");
   cudaStream_t st = (cudaStream_t)stream;
   EncodeArgs a{pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, residual_out, stage_sqerr, flags};
-  const bool want_tc = tc_shape(K, D) && !(flags & (RVQ_FLAG_FORCE_EXACT | RVQ_FLAG_DIRECT_DIST));
+  const bool want_tc = tc_shape(K, D) && !(flags & RVQ_FLAG_FORCE_EXACT);
   return want_tc ? tc_encode(a, st) : simt_encode(a, st);
 }
 
@@ -101,9 +101,10 @@ int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int6
   RVQ_REQUIRE(N >= 0 && N < (int64_t(1) << 31), "rvq_kmeans_assign: N out of range");
   if (N == 0) return RVQ_OK;
   // samples [N, D] viewed as x[B=1, D, T=N] with strides (0, 1, D)
-  EncodeArgs a{pack, K, D, samples, 0, 1, D, 1, (int)N, 0, 1, buckets, nullptr, nullptr, nullptr,
-               RVQ_FLAG_DIRECT_DIST | RVQ_FLAG_FORCE_EXACT};
-  return simt_encode(a, (cudaStream_t)stream);
+  // the assignment is the search's contraction: on the tensor cores where the shape allows, exact fp32 re-scores with the
+  // direct distance of core_vq.py:86-88 (ties -> lowest index); other shapes take the fp32 SIMT kernel
+  EncodeArgs a{pack, K, D, samples, 0, 1, D, 1, (int)N, 0, 1, buckets, nullptr, nullptr, nullptr, RVQ_FLAG_DIRECT_DIST};
+  return tc_shape(K, D) ? tc_encode(a, (cudaStream_t)stream) : simt_encode(a, (cudaStream_t)stream);
 }
 
 /* debug only (not part of the public header): timeline of CTA 0 of the last tcgen05 encode (RVQ_TC_TRACE builds) */

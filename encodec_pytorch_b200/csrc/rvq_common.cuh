@@ -21,6 +21,7 @@ namespace rvq {
 //     tc      fp16 image     (only D==128 && K%128==0) K/128 chunks of 36864 B, each the
 //                            shared-memory image of a 128-code x 144-K UMMA B operand
 //     meta    StageMeta
+//     outl    u8 [K]         1 = code excluded from the fp16 image (outlier norm / fp16 range)
 // ----------------------------------------------------------------------------------------------
 constexpr int kHeaderBytes  = 256;
 constexpr int kTcChunkCodes = 128;                 // codes per UMMA N tile
@@ -51,7 +52,7 @@ __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~size_
 __host__ __device__ inline bool tc_shape(int K, int D) { return D == 128 && K >= kTcChunkCodes && K <= 1024 && (K % kTcChunkCodes) == 0; }
 
 struct StageLayout {
-  size_t off_tab32, off_tab32T, off_cnorm, off_tc, off_meta, stride;
+  size_t off_tab32, off_tab32T, off_cnorm, off_tc, off_meta, off_outl, stride;
 };
 __host__ __device__ inline StageLayout stage_layout(int K, int D) {
   StageLayout L;
@@ -61,6 +62,7 @@ __host__ __device__ inline StageLayout stage_layout(int K, int D) {
   L.off_cnorm = o;  o += align256(size_t(K) * 4);
   L.off_tc = o;     o += tc_shape(K, D) ? size_t(K / kTcChunkCodes) * kTcChunkBytes : 0;
   L.off_meta = o;   o += 256;
+  L.off_outl = o;   o += tc_shape(K, D) ? align256(size_t(K)) : 0;      // u8 [K]: codes excluded from the fp16 image
   L.stride = o;
   return L;
 }
@@ -75,6 +77,7 @@ struct PackView {
   __host__ __device__ const float* cnorm(int s)  const { return (const float*)(stage(s) + L.off_cnorm); }
   __host__ __device__ const unsigned char* tc(int s) const { return stage(s) + L.off_tc; }
   __host__ __device__ const StageMeta* meta(int s) const { return (const StageMeta*)(stage(s) + L.off_meta); }
+  __host__ __device__ const unsigned char* outl(int s) const { return stage(s) + L.off_outl; }
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -114,6 +117,14 @@ struct FrameAddr {
 __device__ __forceinline__ bool nan_aware_better(float dist, int code, float best, int bcode) {
   if (dist != dist) return best == best || code < bcode;
   return best == best && (dist < best || (dist == best && code < bcode));
+}
+
+// element index of the code of (stage s of the call, frame n) in the codes output: [n_q, B, T] by default,
+// [B, n_q, T] with RVQ_FLAG_CODES_BKT (n < 2^31)
+__device__ __forceinline__ int64_t code_index(int bkt, int n_q, int T, int64_t N, int s, int64_t n) {
+  if (!bkt) return int64_t(s) * N + n;
+  const uint32_t b = uint32_t(n) / uint32_t(T), t = uint32_t(n) - b * uint32_t(T);
+  return (int64_t(b) * n_q + s) * T + t;
 }
 
 // optional search counters of the calling thread (rvq_search_counters); nullptr = off

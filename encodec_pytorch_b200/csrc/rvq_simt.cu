@@ -153,18 +153,30 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     m.xlimit = xl > 0.f ? xl : 0.f;
     *const_cast<StageMeta*>(pv.meta(s)) = m;
   }
-  // fp16 image (layout in rvq_common.cuh): chunk c = 128 codes x 18 K-groups of 8 halves
+  // the flags go to the pack: pack_image_kernel (many blocks per stage) builds the fp16 image from them
+  unsigned char* og = const_cast<unsigned char*>(pv.outl(s));
+  for (int k = threadIdx.x; k < K; k += blockDim.x) og[k] = outl[k];
+}
+
+// fp16 UMMA image of a stage (layout in rvq_common.cuh): chunk c = 128 codes x 18 K-groups of 8 halves.  grid (stages, 18):
+// a block writes one K-group of every code (consecutive threads -> consecutive codes -> contiguous 16 B).
+__global__ void __launch_bounds__(256) pack_image_kernel(unsigned char* pack, int stage_base, int K, int D) {
+  const int s = stage_base + blockIdx.x, g = blockIdx.y;
+  PackView pv(pack, K, D);
+  const float* t32 = pv.tab32(s);
+  const float* cn = pv.cnorm(s);
+  const unsigned char* outl = pv.outl(s);
   unsigned char* img = const_cast<unsigned char*>(pv.tc(s));
-  const int ngroups = kTcKPad / 8;   // 18
-  for (int i = threadIdx.x; i < K * ngroups; i += blockDim.x) {
-    int g = i / K, k = i - g * K;     // consecutive threads -> consecutive codes -> contiguous 16 B
-    int c = k / kTcChunkCodes, r = k % kTcChunkCodes;
-    bool o = outl[k] != 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int c = k / kTcChunkCodes, r = k % kTcChunkCodes;
+    const bool o = outl[k] != 0;
     __align__(16) __half h[8];
     if (g < 16) {
-      const float* row = t32 + size_t(k) * D + g * 8;
+      const float4* row = reinterpret_cast<const float4*>(t32 + size_t(k) * D + g * 8);
+      const float4 a = row[0], b = row[1];
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
       #pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(o ? 0.f : -2.f * row[j]);
+      for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(o ? 0.f : -2.f * v[j]);
     } else if (g == 16) {
       float ee = o ? kBigScore : cn[k];
       __half hi = __float2half_rn(ee);
@@ -197,6 +209,10 @@ int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* 
     RVQ_LAUNCH_CHECK("pack_copy_kernel");
     pack_meta_kernel<<<ns, 1024, meta_smem, st>>>((unsigned char*)pack, s0, K, D, margin_scale);
     RVQ_LAUNCH_CHECK("pack_meta_kernel");
+    if (tc_shape(K, D)) {
+      pack_image_kernel<<<dim3(ns, kTcKPad / 8), 256, 0, st>>>((unsigned char*)pack, s0, K, D);
+      RVQ_LAUNCH_CHECK("pack_image_kernel");
+    }
   }
   return RVQ_OK;
 }
@@ -213,7 +229,7 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
                     const float* __restrict__ x, FrameAddr fa, int64_t N,
                     int stage0, int n_q, int64_t* __restrict__ codes,
                     float* __restrict__ quantized, float* __restrict__ residual_out,
-                    double* __restrict__ sqerr, int ste, int accum_q) {
+                    double* __restrict__ sqerr, int ste, int accum_q, int bkt, int bdt) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                    // [D][64] residual, frame-contiguous
   float* cs = xs + size_t(D) * kXF;    // [D][64] codebook chunk, code-contiguous
@@ -243,11 +259,18 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
     }
     xpart[uq * kXF + uf] = part;
   }
+  // element of frame n, dim d of the fp32 frame output: [B, T, D], or [B, D, T] with RVQ_FLAG_OUT_BDT
+  auto qidx = [&](int64_t n, int d) -> int64_t {
+    if (!bdt) return n * D + d;
+    const int64_t b = n / fa.T, t = n - b * fa.T;
+    return (b * D + d) * fa.T + t;
+  };
   if (quantized != nullptr) {
     if (accum_q) {
       for (int i = tid; i < kXF * D; i += 256) {
-        int f = i / D, d = i - f * D;
-        qs[d * kXF + f] = (n0 + f < N) ? quantized[(n0 + f) * D + d] : 0.f;
+        int f, d;
+        if (bdt) { d = i / kXF; f = i - d * kXF; } else { f = i / D; d = i - f * D; }
+        qs[d * kXF + f] = (n0 + f < N) ? quantized[qidx(n0 + f, d)] : 0.f;
       }
     } else {
       for (int d = uq * dq; d < (uq + 1) * dq; ++d) qs[d * kXF + uf] = 0.f;
@@ -339,7 +362,7 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
         if (quantized != nullptr) qs[d * kXF + uf] += q;
       }
       xpart[uq * kXF + uf] = part;
-      if (uvalid && uq == 0) codes[int64_t(si) * N + un] = idx;
+      if (uvalid && uq == 0) codes[code_index(bkt, n_q, fa.T, N, si, un)] = idx;
       if (sqerr != nullptr) {
         float v = uvalid ? part : 0.f;
         #pragma unroll
@@ -359,8 +382,9 @@ exact_encode_kernel(const unsigned char* pack, int K, int D,
   // frame-major stores: consecutive threads write consecutive dims of one frame
   if (quantized != nullptr) {
     for (int i = tid; i < kXF * D; i += 256) {
-      int f = i / D, d = i - f * D;
-      if (n0 + f < N) quantized[(n0 + f) * D + d] = qs[d * kXF + f];
+      int f, d;
+      if (bdt) { d = i / kXF; f = i - d * kXF; } else { f = i / D; d = i - f * D; }      // consecutive threads -> consecutive addresses
+      if (n0 + f < N) quantized[qidx(n0 + f, d)] = qs[d * kXF + f];
     }
   }
   if (residual_out != nullptr) {
@@ -385,7 +409,8 @@ int simt_encode(const EncodeArgs& a, cudaStream_t st) {
   RVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, 256, smem, st>>>((const unsigned char*)a.pack, K, D, a.x, fa, N, a.stage0, a.n_q, a.codes,
                                 a.quantized, a.residual_out, a.sqerr, (a.flags & RVQ_FLAG_STE) ? 1 : 0,
-                                (a.flags & RVQ_FLAG_ACCUM_Q) ? 1 : 0);
+                                (a.flags & RVQ_FLAG_ACCUM_Q) ? 1 : 0, (a.flags & RVQ_FLAG_CODES_BKT) ? 1 : 0,
+                                (a.flags & RVQ_FLAG_OUT_BDT) ? 1 : 0);
   RVQ_LAUNCH_CHECK("exact_encode_kernel");
   return RVQ_OK;
 }
@@ -466,6 +491,73 @@ chain_kernel(const unsigned char* pack, int K, int D,
   }
 }
 
+// decode / quantized sum with the output written as contiguous [B, D, T] (RVQ_FLAG_OUT_BDT): a block takes 32 consecutive
+// frames (a warp walks the stages of four of them exactly like chain_kernel), parks the sums in a transposed shared-memory
+// tile and writes 128-byte runs along t.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+chain_bdt_kernel(const unsigned char* pack, int K, int D,
+                 const float* __restrict__ x, FrameAddr fa, int64_t N, int stage0, int n_q,
+                 const int64_t* __restrict__ codes, int64_t scq, int64_t scb, int64_t sct, int T,
+                 float* __restrict__ out, int ste, int accum) {
+  extern __shared__ float tile[];            // [D][33]
+  PackView pv(pack, K, D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nd4 = D >> 2;
+  for (int64_t n0 = int64_t(blockIdx.x) * 32; n0 < N; n0 += int64_t(gridDim.x) * 32) {
+    for (int fl = warp; fl < 32; fl += 8) {
+      const int64_t n = n0 + fl;
+      if (n >= N) break;
+      const int64_t b = n / T, t = n - b * T;
+      for (int g0 = 0; g0 < nd4; g0 += 32) {
+        const int g = g0 + lane;
+        const bool act = g < nd4;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f), acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == kQuantSum && accum && act) {      // the running sum continues in stage order (same association as one call)
+          const float* o = out + (b * D + g * 4) * T + t;
+          acc = make_float4(o[0], o[T], o[2 * int64_t(T)], o[3 * int64_t(T)]);
+        }
+        if (MODE == kQuantSum && ste && act) {
+          const int64_t xb = fa.base(n) + int64_t(g) * 4 * fa.sxd;
+          r.x = x[xb]; r.y = x[xb + fa.sxd]; r.z = x[xb + 2 * fa.sxd]; r.w = x[xb + 3 * fa.sxd];
+        }
+        for (int s0 = 0; s0 < n_q; s0 += 32) {
+          int mycode = 0;
+          if (s0 + lane < n_q) {
+            int64_t c = codes[int64_t(s0 + lane) * scq + b * scb + t * sct];
+            mycode = c < 0 ? 0 : (c >= K ? K - 1 : int(c));
+          }
+          const int ns = n_q - s0 < 32 ? n_q - s0 : 32;
+          for (int i = 0; i < ns; ++i) {
+            const int idx = __shfl_sync(0xffffffffu, mycode, i);
+            if (!act) continue;
+            float4 q = *reinterpret_cast<const float4*>(pv.tab32(stage0 + s0 + i) + size_t(idx) * D + g * 4);
+            if (MODE == kQuantSum && ste) {
+              q.x = r.x + (q.x - r.x); q.y = r.y + (q.y - r.y); q.z = r.z + (q.z - r.z); q.w = r.w + (q.w - r.w);
+              r.x -= q.x; r.y -= q.y; r.z -= q.z; r.w -= q.w;
+            }
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+          }
+        }
+        if (act) {
+          float* tp = tile + (g * 4) * 33 + fl;
+          tp[0] = acc.x; tp[33] = acc.y; tp[66] = acc.z; tp[99] = acc.w;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D * 32; i += 256) {
+      const int d = i >> 5, fl = i & 31;
+      const int64_t n = n0 + fl;
+      if (n < N) {
+        const int64_t b = n / T, t = n - b * T;
+        out[(b * D + d) * T + t] = tile[d * 33 + fl];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 static unsigned chain_grid(int64_t N) {
   int64_t blocks = (N + 7) / 8;              // 8 warps per block, one frame per warp per pass
   const int64_t cap = 148 * 16;              // persistent-ish: a few waves over 148 SMs
@@ -475,10 +567,27 @@ static unsigned chain_grid(int64_t N) {
 
 // quantized [N, D] = (accum ? quantized : 0) + sum over stages of the gathered rows (or of the
 // straight-through values), in stage order; companion launch of the tensor-core search
+static unsigned chain_bdt_grid(int64_t N) {
+  int64_t blocks = (N + 31) / 32;
+  const int64_t cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  return unsigned(blocks < 1 ? 1 : blocks);
+}
+
 int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa, int64_t N, int T, int stage0, int n_q,
-                   const int64_t* codes, float* out, int ste, int accum, cudaStream_t st) {
+                   const int64_t* codes, float* out, int flags, cudaStream_t st) {
+  const int ste = (flags & RVQ_FLAG_STE) ? 1 : 0, accum = (flags & RVQ_FLAG_ACCUM_Q) ? 1 : 0;
+  // codes as the search wrote them: [n_q, B, T] or, with RVQ_FLAG_CODES_BKT, [B, n_q, T]
+  const bool bkt = (flags & RVQ_FLAG_CODES_BKT) != 0;
+  const int64_t scq = bkt ? int64_t(T) : N, scb = bkt ? int64_t(n_q) * T : int64_t(T);
+  if (flags & RVQ_FLAG_OUT_BDT) {
+    chain_bdt_kernel<kQuantSum><<<chain_bdt_grid(N), 256, size_t(D) * 33 * 4, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0,
+                                                                                 n_q, codes, scq, scb, 1, T, out, ste, accum);
+    RVQ_LAUNCH_CHECK("chain_bdt_kernel<quant_sum>");
+    return RVQ_OK;
+  }
   chain_kernel<kQuantSum><<<chain_grid(N), 256, 0, st>>>((const unsigned char*)pack, K, D, x, fa, N, stage0, n_q, codes,
-                                                        N, T, 1, T, nullptr, out, nullptr, nullptr, ste, accum);
+                                                        scq, scb, 1, T, nullptr, out, nullptr, nullptr, ste, accum);
   RVQ_LAUNCH_CHECK("chain_kernel<quant_sum>");
   return RVQ_OK;
 }
@@ -697,6 +806,11 @@ extern "C" {
 
 int rvq_decode(const void* pack, int K, int D, const int64_t* codes, int64_t scq, int64_t scb, int64_t sct,
                int n_q, int B, int T, float* out, void* stream) {
+  return rvq_decode_ex(pack, K, D, codes, scq, scb, sct, n_q, B, T, out, 0, stream);
+}
+
+int rvq_decode_ex(const void* pack, int K, int D, const int64_t* codes, int64_t scq, int64_t scb, int64_t sct,
+                  int n_q, int B, int T, float* out, int flags, void* stream) {
   if (int e = check_device()) return e;
   RVQ_REQUIRE(D % 4 == 0 && D > 0 && K > 0 && n_q >= 0 && B >= 0 && T >= 0, "rvq_decode: bad shape K=%d D=%d n_q=%d", K, D, n_q);
   const int64_t N = int64_t(B) * T;
@@ -704,6 +818,13 @@ int rvq_decode(const void* pack, int K, int D, const int64_t* codes, int64_t scq
   RVQ_REQUIRE(pack && out && (codes || n_q == 0), "rvq_decode: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   FrameAddr fa{0, 0, 0, T};
+  if (flags & RVQ_FLAG_OUT_BDT) {
+    RVQ_REQUIRE(D <= 256, "rvq_decode: dimension %d too large for the [B, D, T] output path", D);
+    chain_bdt_kernel<kDecode><<<chain_bdt_grid(N), 256, size_t(D) * 33 * 4, st>>>((const unsigned char*)pack, K, D, nullptr, fa, N, 0, n_q,
+                                                                               codes, scq, scb, sct, T, out, 0, 0);
+    RVQ_LAUNCH_CHECK("chain_bdt_kernel<decode>");
+    return RVQ_OK;
+  }
   chain_kernel<kDecode><<<chain_grid(N), 256, 0, st>>>((const unsigned char*)pack, K, D, nullptr, fa, N, 0, n_q,
                                                       codes, scq, scb, sct, T, nullptr, out, nullptr, nullptr, 0);
   RVQ_LAUNCH_CHECK("chain_kernel<decode>");

@@ -116,6 +116,8 @@ struct TcParams {
   int stage0, n_q;
   int64_t* codes; float* residual_out; double* sqerr;
   int ste;
+  int bkt;                 // codes as [B, n_q, T] (RVQ_FLAG_CODES_BKT)
+  int direct;              // exact re-scores use the k-means distance sum((x - c)^2) of core_vq.py:86-91 (RVQ_FLAG_DIRECT_DIST)
   int tf;                  // frames per tile (<= 128): chosen by the host so that every CTA gets an even number of tiles
   unsigned long long* counters;
 };
@@ -137,6 +139,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+// sum of squared differences of two float4 (the k-means distance of core_vq.py:86-88)
+__device__ __forceinline__ float sqd4(const float4& a, const float4& b, float acc) {
+  const float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z, w = a.w - b.w;
+  acc = fmaf(x, x, acc); acc = fmaf(y, y, acc); acc = fmaf(z, z, acc); return fmaf(w, w, acc);
 }
 __device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
   float t[11];
@@ -193,22 +200,34 @@ __device__ __forceinline__ void pair_min(const uint32_t (&u)[16], const uint32_t
 // the whole warp scores the table, one code per lane, stores the code and rewrites the frame's entry as a
 // certified winner for the update warps.
 __device__ __forceinline__ void resolve_full(const float* rs, unsigned char* ms, int f, int lane, int K, const float* __restrict__ t32,
-                                          const float* __restrict__ cn, int64_t* code_out) {
+                                          const float* __restrict__ cn, int64_t* code_out, bool direct) {
   const float4 rl = *reinterpret_cast<const float4*>(rs + rs_off(f, lane));
   const float rr = warp_sum(dot4(rl, rl, 0.f));
   float best = inf_f(); int bcode = 0x7fffffff;
   for (int code = lane; code < K; code += 32) {
     const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(code) * 128);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    #pragma unroll 2
-    for (int ch = 0; ch < 32; ch += 4) {
-      a0 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 0)), __ldg(rp + ch + 0), a0);
-      a1 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 1)), __ldg(rp + ch + 1), a1);
-      a2 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 2)), __ldg(rp + ch + 2), a2);
-      a3 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 3)), __ldg(rp + ch + 3), a3);
+    float dist;
+    if (direct) {
+      #pragma unroll 2
+      for (int ch = 0; ch < 32; ch += 4) {
+        a0 = sqd4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 0)), __ldg(rp + ch + 0), a0);
+        a1 = sqd4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 1)), __ldg(rp + ch + 1), a1);
+        a2 = sqd4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 2)), __ldg(rp + ch + 2), a2);
+        a3 = sqd4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 3)), __ldg(rp + ch + 3), a3);
+      }
+      dist = (a0 + a1) + (a2 + a3);                                    // core_vq.py:86-88
+    } else {
+      #pragma unroll 2
+      for (int ch = 0; ch < 32; ch += 4) {
+        a0 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 0)), __ldg(rp + ch + 0), a0);
+        a1 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 1)), __ldg(rp + ch + 1), a1);
+        a2 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 2)), __ldg(rp + ch + 2), a2);
+        a3 = dot4(*reinterpret_cast<const float4*>(rs + rs_off(f, ch + 3)), __ldg(rp + ch + 3), a3);
+      }
+      const float dot = (a0 + a1) + (a2 + a3);
+      dist = (rr - 2.f * dot) + __ldg(cn + code);                      // core_vq.py:183-187
     }
-    const float dot = (a0 + a1) + (a2 + a3);
-    const float dist = (rr - 2.f * dot) + __ldg(cn + code);          // core_vq.py:183-187
     if (nan_aware_better(dist, code, best, bcode)) { best = dist; bcode = code; }
   }
   #pragma unroll
@@ -282,10 +301,12 @@ __device__ __forceinline__ void load_cand(Cand<NC>& k, int j, const float* __res
 }
 // exact distances of up to NC candidates (core_vq.py:183-187); keeps the best (lowest code on ties) and its slot u
 template <int NC>
-__device__ __forceinline__ void score_cand(const Cand<NC>& k, const Row4& r, float rr, float& best, int& bcode, int& bidx) {
+__device__ __forceinline__ void score_cand(const Cand<NC>& k, const Row4& r, float rr, float& best, int& bcode, int& bidx, bool direct) {
   float d[NC];
   #pragma unroll
-  for (int u = 0; u < NC; ++u) d[u] = dot_row(r, k.w[u]);
+  for (int u = 0; u < NC; ++u)
+    d[u] = direct ? (sqd4(r.v[0], k.w[u].v[0], 0.f) + sqd4(r.v[1], k.w[u].v[1], 0.f)) + (sqd4(r.v[2], k.w[u].v[2], 0.f) + sqd4(r.v[3], k.w[u].v[3], 0.f))
+                  : dot_row(r, k.w[u]);
   #pragma unroll
   for (int off = 4; off > 0; off >>= 1) {
     #pragma unroll
@@ -293,7 +314,7 @@ __device__ __forceinline__ void score_cand(const Cand<NC>& k, const Row4& r, flo
   }
   #pragma unroll
   for (int u = 0; u < NC; ++u) {
-    const float e = (rr - 2.f * d[u]) + k.nrm[u];
+    const float e = direct ? d[u] : (rr - 2.f * d[u]) + k.nrm[u];
     if (k.c[u] >= 0 && (e < best || (e == best && k.c[u] < bcode))) { best = e; bcode = k.c[u]; bidx = u; }
   }
 }
@@ -327,7 +348,7 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
         k.c[u] = (a >= 0 && jj >= 0) ? code_of(a, jj, rot, nchunks) : -1;
       }
       load_cand<2>(k, j, t32, cn);
-      score_cand<2>(k, r, rr, best, bcode, bidx);
+      score_cand<2>(k, r, rr, best, bcode, bidx, TRAIN && p.direct);
     }
   }
   // best over the four quarters (candidate codes are distinct, so the winner's quarter is unique)
@@ -346,7 +367,7 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
   const int64_t nfr = tile_n0 + f;
   if (mine && j == 0) {
     *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;      // the frame now has a single (exact) winner
-    if (f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
+    if (f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = bcode;
   }
 }
 
@@ -416,8 +437,10 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     it.n2 = it.cd.z >= 0 ? __ldg(cn + it.cd.z) : 0.f; it.n3 = it.cd.w >= 0 ? __ldg(cn + it.cd.w) : 0.f;
   };
   auto item_finish = [&](const Item& it) {
-    float rr = dot4(it.rl, it.rl, 0.f), d0 = dot4(it.rl, it.w0, 0.f), d1 = dot4(it.rl, it.w1, 0.f), d2 = dot4(it.rl, it.w2, 0.f),
-          d3 = dot4(it.rl, it.w3, 0.f);
+    const bool direct = TRAIN && p.direct;
+    float rr = dot4(it.rl, it.rl, 0.f), d0, d1, d2, d3;
+    if (direct) { d0 = sqd4(it.rl, it.w0, 0.f); d1 = sqd4(it.rl, it.w1, 0.f); d2 = sqd4(it.rl, it.w2, 0.f); d3 = sqd4(it.rl, it.w3, 0.f); }
+    else { d0 = dot4(it.rl, it.w0, 0.f); d1 = dot4(it.rl, it.w1, 0.f); d2 = dot4(it.rl, it.w2, 0.f); d3 = dot4(it.rl, it.w3, 0.f); }
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       rr += __shfl_xor_sync(0xffffffffu, rr, off);
@@ -426,7 +449,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     }
     float best = inf_f(); int bcode = 0x7fffffff; float4 wsel = it.w0;     // NaN distances only: the first candidate
     auto consider = [&](float d, float nrm, int code, const float4& w) {
-      const float e = (rr - 2.f * d) + nrm;
+      const float e = direct ? d : (rr - 2.f * d) + nrm;
       if (code >= 0 && (e < best || (e == best && code < bcode))) { best = e; bcode = code; wsel = w; }
     };
     consider(d0, it.n0, it.cd.x, it.w0); consider(d1, it.n1, it.cd.y, it.w1);
@@ -436,10 +459,24 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     const int64_t nfr = tile_n0 + it.f;
     if (lane == 0) {
       *reinterpret_cast<int*>(ms + Sm::m_cand + it.f * 16) = bcode;
-      if (it.f < p.tf && nfr < p.N) p.codes[int64_t(s) * p.N + nfr] = bcode;
+      if (it.f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = bcode;
     }
   };
-  Item it;
+  // Listed frames FIRST, up to two per warp in flight at once (their candidate rows are the only loads of the warp at
+  // that point: one L2 round trip for all of them instead of one per frame queued behind the 64 winner rows), then the
+  // winner rows of the certified frames, which fly while the warps meet at the barrier.
+  if (nslow + nwide > 0) {
+    #pragma unroll 1
+    for (int i = u; i < nslow; i += kUpdWarps) {
+      Item it0;
+      item_load(i, it0);
+      item_finish(it0);
+    }
+    // wide candidate sets: one frame per warp at a time, handed out from the last warp down
+    #pragma unroll 1
+    for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
+    RVQ_TRACE3(trX, trn, u, 1);
+  }
   float4 qa[8], qb[8];
   {
     const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
@@ -450,12 +487,6 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     for (int i = 0; i < 8; ++i) qb[i] = nB == 1 ? __ldg(rb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (nslow + nwide > 0) {
-    #pragma unroll 1
-    for (int i = u; i < nslow; i += kUpdWarps) { item_load(i, it); item_finish(it); }
-    // wide candidate sets: one frame per warp at a time, handed out from the last warp down
-    #pragma unroll 1
-    for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
-    RVQ_TRACE3(trX, trn, u, 1);
     ptx::named_bar_sync(6, kUpdWarps * 32);      // listed frames are updated, wide frames have their winner
     RVQ_TRACE3(trX, trn, u, 2);
     if (nwide > 0 && __any_sync(0xffffffffu, nA == kBig || nB == kBig)) {
@@ -908,7 +939,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
         *reinterpret_cast<uint32_t*>(ms + Sm::m_cmask + f * 4) = cmask;
         *reinterpret_cast<uint32_t*>(ms + Sm::m_bmask + f * 4) = bmask;
-        int64_t* code_out = (f < p.tf && nfr < p.N) ? p.codes + int64_t(s) * p.N + nfr : nullptr;
+        int64_t* code_out = (f < p.tf && nfr < p.N) ? p.codes + code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr) : nullptr;
         if (!full && ncand == 1 && code_out != nullptr) *code_out = cd.x;      // certified: the warp's codes are one 256-byte run
         {
           int* qc = reinterpret_cast<int*>(ms + Sm::m_qcnt);
@@ -921,7 +952,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           while (fm) {
             const int i = __ffs(fm) - 1; fm &= fm - 1;
             int64_t* co = reinterpret_cast<int64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)code_out, i));
-            resolve_full(rs, ms, q * 32 + i, lane, p.K, t32, cn, co);
+            resolve_full(rs, ms, q * 32 + i, lane, p.K, t32, cn, co, TRAIN && p.direct);
           }
         }
         n_full += full ? 1u : 0u; n_cert += (!full && ncand == 1) ? 1u : 0u; n_resc += (!full && ncand > 1) ? 1u : 0u;
@@ -970,7 +1001,7 @@ int tc_debug_trace(long long* out_host, int n) {
 }
 
 int simt_quant_sum(const void* pack, int K, int D, const float* x, FrameAddr fa, int64_t N, int T, int stage0, int n_q,
-                   const int64_t* codes, float* out, int ste, int accum, cudaStream_t st);
+                   const int64_t* codes, float* out, int flags, cudaStream_t st);
 
 int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   const int64_t N = int64_t(a.B) * a.T;
@@ -991,6 +1022,8 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   p.stage0 = a.stage0; p.n_q = a.n_q;
   p.codes = a.codes; p.residual_out = a.residual_out; p.sqerr = a.sqerr;
   p.ste = (a.flags & RVQ_FLAG_STE) ? 1 : 0;
+  p.bkt = (a.flags & RVQ_FLAG_CODES_BKT) ? 1 : 0;
+  p.direct = (a.flags & RVQ_FLAG_DIRECT_DIST) ? 1 : 0;
   p.counters = search_counters();     // nullptr unless the caller registered a buffer (rvq_search_counters)
   // full 128-frame tiles: a CTA's odd last tile runs alone (measured on B200 at cfg2: 0.62 ms against 0.67 ms for balanced
   // 82-frame tiles, whose MMAs cost the same as full ones)
@@ -1002,12 +1035,11 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   const unsigned grid = unsigned(ntiles < sm_count ? ntiles : sm_count);
   // the lean variant serves plain encodes; straight-through arithmetic, loss numerators and the residual output
   // live in the other one (a stage's hot code has to fit the instruction cache)
-  if (p.ste || p.sqerr != nullptr || p.residual_out != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, Sm::total, st>>>(p);
+  if (p.ste || p.direct || p.sqerr != nullptr || p.residual_out != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, Sm::total, st>>>(p);
   else tc_encode_kernel<false><<<grid, kThreadsTc, Sm::total, st>>>(p);
   RVQ_LAUNCH_CHECK("tc_encode_kernel");
   if (a.quantized != nullptr)
-    return simt_quant_sum(a.pack, a.K, a.D, a.x, p.fa, N, a.T, a.stage0, a.n_q, a.codes, a.quantized, p.ste,
-                          (a.flags & RVQ_FLAG_ACCUM_Q) ? 1 : 0, st);
+    return simt_quant_sum(a.pack, a.K, a.D, a.x, p.fa, N, a.T, a.stage0, a.n_q, a.codes, a.quantized, a.flags, st);
   return RVQ_OK;
 }
 

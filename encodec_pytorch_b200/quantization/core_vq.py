@@ -332,6 +332,10 @@ def _warn_issue25() -> None:
                   'The bug wasn\'t fixed here for reproducibility.')
 
 
+# Run the (provably overwritten) dead-code expiry kernels inside the training forward anyway -- for fidelity experiments.
+RUN_DEAD_EXPIRY = False
+
+
 def _rng_stream(device: torch.device, n: int) -> tp.Tuple[int, int]:
     """(seed, offset) of the device's global torch generator for a device-side draw, advancing it like a
     torch random op would (``torch.manual_seed`` therefore reproduces the draws)."""
@@ -352,6 +356,13 @@ def _expire_stack(layers: tp.Sequence[VectorQuantization], pk: ops.CodebookPack,
     thr = cbs[0].threshold_ema_dead_code
     if thr == 0:
         return
+    if not RUN_DEAD_EXPIRY:
+        # core_vq.py:226 replaces dead rows of `embed`, core_vq.py:235 then overwrites EVERY row of `embed` with
+        # embed_avg / smoothed cluster_size in the same call, and nothing in between reads `embed`: inside
+        # a training forward the expiry cannot change any buffer.  Its launches are therefore skipped; the device generator
+        # still advances as if the draw had happened.  (EuclideanCodebook.expire_codes_ called on its own does replace rows.)
+        _rng_stream(x.device, len(cbs))
+        return
     if 2 * cbs[0].codebook_size <= 4096:
         seed, off = _rng_stream(x.device, len(cbs))
         ops.expire_stack(pk, x, codes, stage0, [cb.cluster_size for cb in cbs], [cb.embed for cb in cbs],
@@ -370,7 +381,7 @@ def _expire_stack(layers: tp.Sequence[VectorQuantization], pk: ops.CodebookPack,
 
 
 def _stack_forward(layers: tp.Sequence[VectorQuantization], x: torch.Tensor, n_q: int, training: bool,
-                   stack_pack: tp.Optional[tp.Callable[[], ops.CodebookPack]] = None):
+                   stack_pack: tp.Optional[tp.Callable[[], ops.CodebookPack]] = None, out_bdt: bool = False):
     """Forward of a residual stack of plain (un-projected) layers: core_vq.py:337-355 over
     :301-324 over :212-237.  Steady state is one fused launch for all ``n_q`` stages; a stage
     whose codebook still needs its k-means init forces that step to run stage by stage
@@ -390,12 +401,20 @@ def _stack_forward(layers: tp.Sequence[VectorQuantization], x: torch.Tensor, n_q
 
     if all(cb._is_inited() for cb in cbs):
         pk = stack_pack() if stack_pack is not None else ops.pack([cb.embed for cb in cbs])
-        codes, quant, sqerr, _ = ops.encode(pk, xd, 0, n_q, want_quantized=True,
-                                            want_sqerr=training and cw > 0, flags=flags)
         if training:
+            # The sum of the straight-through values telescopes: sum_i ste_i = x - r_final (each stage subtracts what it
+            # adds, core_vq.py:348-349), so the fused search hands back its final residual and the quantized sum is one
+            # elementwise pass instead of a second walk over all stages' rows; fp32 rounding differs from the reference's
+            # running sum by a few ulp (<< the 1e-5 bar).  Eval keeps the ordered sum of gathered rows (bit-exact).
+            codes, _, sqerr, res = ops.encode(pk, xd, 0, n_q, want_sqerr=cw > 0, want_residual=True, flags=flags)
+            quant = (xd - res.permute(0, 2, 1)) if out_bdt else (xd.permute(0, 2, 1) - res)
+            if out_bdt and not quant.is_contiguous():
+                quant = quant.contiguous()
             with torch.no_grad():
                 _expire_stack(layers, pk, xd, codes, 0, flags)
                 _update_stack(cbs, pk, xd, codes, 0, flags)
+        else:
+            codes, quant, sqerr, _ = ops.encode(pk, xd, 0, n_q, want_quantized=True, flags=flags, out_bdt=out_bdt)
     else:
         # first step(s): stage i's init needs stage i-1's fresh quantisation -> sequential
         quant = torch.zeros((b, t, d), dtype=torch.float32, device=x.device)
@@ -418,12 +437,16 @@ def _stack_forward(layers: tp.Sequence[VectorQuantization], x: torch.Tensor, n_q
         codes = torch.cat(code_list, 0)
         sqerr = torch.cat(sq_list, 0) if sq_list[0] is not None else None
         pk = ops.pack(snap) if (training and x.requires_grad) else None
+        if out_bdt:
+            quant = quant.permute(0, 2, 1).contiguous()
 
     if training and cw > 0:
         losses = (sqerr / float(b * t * d)).to(torch.float32).mul_(cw).view(n_q, 1)
     else:
         losses = torch.zeros((n_q, 1), dtype=torch.float32, device=x.device)
-    quantized = quant.permute(0, 2, 1)
+    # [B, D, T]: a permuted view of the [B, T, D] buffer like the reference's rearrange (core_vq.py:322), or -- with
+    # contiguous_outputs -- the contiguous tensor the kernel wrote directly
+    quantized = quant if out_bdt else quant.permute(0, 2, 1)
     if training:
         if x.requires_grad and torch.is_grad_enabled():
             quantized, losses = _AttachGrad.apply(x, quantized, losses, codes, pk, n_q, cw, flags)
@@ -440,6 +463,10 @@ class ResidualVectorQuantization(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList([VectorQuantization(**kwargs) for _ in range(num_quantizers)])
         self._pack_cache: tp.Optional[tp.Tuple[tp.Any, ops.CodebookPack]] = None
+        # False: `quantized` / decode outputs are permuted views of a [B, T, D] buffer, strides as in the reference
+        # (core_vq.py:298, :322).  True: contiguous [B, D, T] tensors written directly by the kernels -- what SEANet's decoder
+        # convolution consumes (modules/seanet.py:193-195) without a re-layout copy.
+        self.contiguous_outputs = False
 
     def _require_plain(self, n: int) -> None:
         for l in self.layers[:n]:
@@ -462,15 +489,18 @@ class ResidualVectorQuantization(nn.Module):
         n_q = n_q or len(self.layers)
         n_q = min(n_q, len(self.layers))           # the reference's slice caps silently (:346)
         self._require_plain(n_q)
-        return _stack_forward(self.layers, x, n_q, self.training, self._stack_pack)
+        return _stack_forward(self.layers, x, n_q, self.training, self._stack_pack, out_bdt=self.contiguous_outputs)
 
-    def encode(self, x: torch.Tensor, n_q: tp.Optional[int] = None) -> torch.Tensor:
-        """core_vq.py:357-367: ``[B, D, T]`` fp32 -> ``[n_q, B, T]`` int64."""
+    def encode(self, x: torch.Tensor, n_q: tp.Optional[int] = None, layout: str = "kbt") -> torch.Tensor:
+        """core_vq.py:357-367: ``[B, D, T]`` fp32 -> ``[n_q, B, T]`` int64.  ``layout="bkt"`` returns the contiguous
+        ``[B, n_q, T]`` tensor that model.py:166 obtains with ``codes.transpose(0, 1)`` (same values, written directly)."""
+        if layout not in ("kbt", "bkt"):
+            raise ValueError(f"layout must be 'kbt' or 'bkt', got {layout!r}")
         n_q = n_q or len(self.layers)
         n_q = min(n_q, len(self.layers))
         self._require_plain(n_q)
         L.require_cuda_f32(x, "x")
-        codes, _, _, _ = ops.encode(self._stack_pack(), x.detach(), 0, n_q)
+        codes, _, _, _ = ops.encode(self._stack_pack(), x.detach(), 0, n_q, codes_bkt=layout == "bkt")
         return codes
 
     def decode(self, q_indices: torch.Tensor) -> torch.Tensor:
@@ -478,4 +508,6 @@ class ResidualVectorQuantization(nn.Module):
         ``[B, D, T]`` fp32, stages summed in order."""
         n = int(q_indices.shape[0])
         self._require_plain(n)
+        if self.contiguous_outputs:
+            return ops.decode(self._stack_pack(), q_indices, out_bdt=True)
         return ops.decode(self._stack_pack(), q_indices).permute(0, 2, 1)

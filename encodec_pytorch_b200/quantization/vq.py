@@ -76,11 +76,53 @@ class ResidualVectorQuantizer(nn.Module):
         """vq.py:110-113."""
         return math.log2(self.bins) * sample_rate / 1000
 
-    def encode(self, x: torch.Tensor, sample_rate: int, bandwidth: tp.Optional[float] = None) -> torch.Tensor:
-        """vq.py:115-122: ``[B, D, T]`` fp32 -> ``[n_q, B, T]`` int64."""
+    def encode(self, x: torch.Tensor, sample_rate: int, bandwidth: tp.Optional[float] = None,
+               layout: str = "kbt") -> torch.Tensor:
+        """vq.py:115-122: ``[B, D, T]`` fp32 -> ``[n_q, B, T]`` int64 (``layout="bkt"``: the contiguous ``[B, n_q, T]``
+        tensor model.py:166 builds with a transpose)."""
         n_q = self.get_num_quantizers_for_bandwidth(sample_rate, bandwidth)
-        return self.vq.encode(x, n_q=n_q)
+        return self.vq.encode(x, n_q=n_q, layout=layout)
 
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
         """vq.py:124-128: ``[n_q, B, T]`` int64 -> ``[B, D, T]`` fp32."""
         return self.vq.decode(codes)
+
+    # ---- the 48 kHz model's segment loop (model.py:141-145 / :178-179) in one launch --------------------------------
+    def encode_segments(self, segments: tp.Sequence[torch.Tensor], sample_rate: int,
+                        bandwidth: tp.Optional[float] = None, layout: str = "kbt") -> tp.List[torch.Tensor]:
+        """``[self.encode(s, sample_rate, bandwidth) for s in segments]`` for latents ``[B, D, T_i]`` of one batch size,
+        with ONE fused launch over all segments: frames are independent (core_vq.py works row-wise on ``[N, D]``), so
+        the segments are laid end to end along time, searched together and the codes handed back as per-segment views
+        (``[n_q, B, T_i]``; ``[B, n_q, T_i]`` with ``layout="bkt"``).  The reference encodes the 31 one-second segments
+        of a 30 s clip one call at a time (4 800 frames each: a quarter of a B200 per launch)."""
+        if len(segments) == 0:
+            return []
+        if len(segments) == 1:
+            return [self.encode(segments[0], sample_rate, bandwidth, layout)]
+        b = segments[0].shape[0]
+        if any(s.dim() != 3 or s.shape[0] != b or s.shape[1] != self.dimension for s in segments):
+            raise RuntimeError("encode_segments: expected latents [B, D, T_i] with a common batch size")
+        lens = [int(s.shape[2]) for s in segments]
+        codes = self.encode(torch.cat(list(segments), dim=2), sample_rate, bandwidth, layout)
+        return list(torch.split(codes, lens, dim=2))
+
+    def decode_segments(self, codes: tp.Sequence[torch.Tensor]) -> tp.List[torch.Tensor]:
+        """``[self.decode(c) for c in codes]`` (codes ``[n_q, B, T_i]``, any strides) with one launch."""
+        if len(codes) <= 1:
+            return [self.decode(c) for c in codes]
+        lens = [int(c.shape[2]) for c in codes]
+        out = self.decode(torch.cat(list(codes), dim=2))
+        return list(torch.split(out, lens, dim=2))
+
+    @property
+    def contiguous_outputs(self) -> bool:
+        """See ``ResidualVectorQuantization.contiguous_outputs``."""
+        return self.vq.contiguous_outputs
+
+    @contiguous_outputs.setter
+    def contiguous_outputs(self, value: bool) -> None:
+        self.vq.contiguous_outputs = bool(value)
+
+    def invalidate(self) -> None:
+        """Forget the cached search image; call after writing codebook buffers through ``.data``."""
+        self.vq.invalidate()

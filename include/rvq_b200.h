@@ -43,6 +43,11 @@ extern "C" {
 #define RVQ_FLAG_FORCE_EXACT  2  /* use the fp32 SIMT search even where the tcgen05 path applies   */
 #define RVQ_FLAG_DIRECT_DIST  4  /* k-means distance sum((x-c)^2) of core_vq.py:86-91 (exact path)  */
 #define RVQ_FLAG_ACCUM_Q      8  /* `quantized` holds a running sum on entry (stage segments)       */
+#define RVQ_FLAG_CODES_BKT   16  /* rvq_encode: codes are written as [B, n_q, T] (what model.py:166 makes of the search's
+                                     [n_q, B, T] with a transpose) instead of [n_q, B, T]                             */
+#define RVQ_FLAG_OUT_BDT     32  /* rvq_encode / rvq_decode_ex: the fp32 frame output (`quantized` / `out`) is written as a
+                                     contiguous [B, D, T] tensor -- the layout SEANet's decoder consumes
+                                     (modules/seanet.py:193-195) -- instead of [B, T, D]                              */
 
 int         rvq_version(void);                 /* RVQ_ABI_VERSION                                    */
 const char* rvq_last_error(void);              /* last error message of the calling thread           */
@@ -63,8 +68,8 @@ int    rvq_pack(const float* const* embed_ptrs_host, int n_q, int K, int D,
  * gather / residual part of .forward (core_vq.py:337-355 with :212-221, :301-324).
  *   x            fp32 [B, D, T] with ELEMENT strides (sxb, sxd, sxt)
  *   stage0,n_q   stages [stage0, stage0+n_q) of the pack are applied in order
- *   codes        int64 [n_q, B, T] contiguous (out)
- *   quantized    fp32 [B, T, D] contiguous (out) or NULL: sum over stages, in stage order, of the
+ *   codes        int64 [n_q, B, T] contiguous (out); [B, n_q, T] with RVQ_FLAG_CODES_BKT
+ *   quantized    fp32 [B, T, D] contiguous (out; [B, D, T] with RVQ_FLAG_OUT_BDT) or NULL: sum over stages, in stage order, of the
  *                gathered codewords (of the straight-through values with RVQ_FLAG_STE)
  *                (RVQ_FLAG_ACCUM_Q: added onto the values already in the buffer)
  *   residual_out fp32 [B, T, D] contiguous (out) or NULL: the residual after the last stage
@@ -82,6 +87,10 @@ int rvq_encode(const void* pack, int K, int D,
 int rvq_decode(const void* pack, int K, int D,
                const int64_t* codes, int64_t scq, int64_t scb, int64_t sct,
                int n_q, int B, int T, float* out, void* stream);
+/* same with flags: RVQ_FLAG_OUT_BDT writes out as contiguous fp32 [B, D, T]                          */
+int rvq_decode_ex(const void* pack, int K, int D,
+                  const int64_t* codes, int64_t scq, int64_t scb, int64_t sct,
+                  int n_q, int B, int T, float* out, int flags, void* stream);
 
 /* ---- EMA statistics: bincount + scatter-add of core_vq.py:227-228 for all stages at once.
  * Re-derives each stage's input residual from x and codes with the encode arithmetic.
