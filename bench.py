@@ -302,7 +302,8 @@ def run_b200(args):
     binding = _bind_near_gpu(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of stdout: one JSON line only
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / warnings go to stderr: stdout is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks = _peaks()
 
