@@ -405,14 +405,27 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   // candidate lists (2..4 codes): one frame per warp at a time, lane = 16-byte chunk of the row, so a frame costs a
   // handful of registers next to the winner rows in flight.  Exact fp32 distances (core_vq.py:183-187), lowest code on
   // ties; the warp holds the winner's row and applies r <- r - q itself.
-  struct Item { int f; int4 cd; float* rp; float4 rl, w0, w1, w2, w3; float n0, n1, n2, n3; };
+  struct Item { int f, ck; int4 cd; float4 rl[4], w[4]; float nrm; };
   auto item_cands = [&](int i, Item& it) {
     it.f = slowq[i];
-    // the 2..4 candidates = flagged batches x flagged classes (warp-uniform enumeration; bit a of the batch mask is the
-    // a-th batch in this CTA's processing order)
-    it.cd = make_int4(-1, -1, -1, -1);
+    // the 2..4 candidates = flagged batches x flagged classes (bit a of the batch mask is the a-th batch in this CTA's
+    // processing order).  Straight-line for the usual case of at most two flagged batches and classes (the first candidate
+    // is always (lowest batch, lowest class), the order of the others does not matter: ties go to the lowest CODE);
+    // three or four flagged classes of one batch (or vice versa) take the generic walk.
     const uint32_t cmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + it.f * 4);
-    uint32_t bm2 = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + it.f * 4);
+    const uint32_t bmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + it.f * 4);
+    const int nc = __popc(cmk), nb = __popc(bmk);
+    if (nc <= 2 && nb <= 2) {
+      const int b0 = __ffs(bmk) - 1, b1 = 31 - __clz(bmk), c0 = __ffs(cmk) - 1, c1 = 31 - __clz(cmk);
+      const bool two = nc == 2 && nb == 2;
+      it.cd.x = code_of(b0, c0, rot, nchunks);
+      it.cd.y = nc == 2 ? code_of(b0, c1, rot, nchunks) : code_of(b1, c0, rot, nchunks);
+      it.cd.z = two ? code_of(b1, c0, rot, nchunks) : -1;
+      it.cd.w = two ? code_of(b1, c1, rot, nchunks) : -1;
+      return;
+    }
+    it.cd = make_int4(-1, -1, -1, -1);
+    uint32_t bm2 = bmk;
     int w = 0;
     while (bm2) {
       const int a = __ffs(bm2) - 1; bm2 &= bm2 - 1;
@@ -424,38 +437,47 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
       }
     }
   };
+  // One candidate per quarter-warp: lane (qq, j) = (lane / 8, lane % 8) holds the chunks 8k + j (k = 0..3) of candidate qq's
+  // row and of the frame's residual row (whole 128-byte lines per load instruction), so a distance needs 3 shuffle levels
+  // and the four candidates are compared with 2 more.
   auto item_load = [&](int i, Item& it) {
     item_cands(i, it);
-    it.rp = rs + rs_off(it.f, lane);
-    it.rl = *reinterpret_cast<const float4*>(it.rp);
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    it.w0 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.x) * 128) + lane);
-    it.w1 = __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.y) * 128) + lane);
-    it.w2 = it.cd.z >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.z) * 128) + lane) : z4;
-    it.w3 = it.cd.w >= 0 ? __ldg(reinterpret_cast<const float4*>(t32 + size_t(it.cd.w) * 128) + lane) : z4;
-    it.n0 = __ldg(cn + it.cd.x); it.n1 = __ldg(cn + it.cd.y);
-    it.n2 = it.cd.z >= 0 ? __ldg(cn + it.cd.z) : 0.f; it.n3 = it.cd.w >= 0 ? __ldg(cn + it.cd.w) : 0.f;
+    const int qq = lane >> 3, j = lane & 7;
+    it.ck = qq == 0 ? it.cd.x : qq == 1 ? it.cd.y : qq == 2 ? it.cd.z : it.cd.w;
+    const float4* rp = reinterpret_cast<const float4*>(t32 + size_t(it.ck < 0 ? 0 : it.ck) * 128) + j;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) it.w[k] = __ldg(rp + 8 * k);
+    it.nrm = __ldg(cn + (it.ck < 0 ? 0 : it.ck));
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) it.rl[k] = *reinterpret_cast<const float4*>(rs + rs_off(it.f, 8 * k + j));
   };
   auto item_finish = [&](const Item& it) {
     const bool direct = TRAIN && p.direct;
-    float rr = dot4(it.rl, it.rl, 0.f), d0, d1, d2, d3;
-    if (direct) { d0 = sqd4(it.rl, it.w0, 0.f); d1 = sqd4(it.rl, it.w1, 0.f); d2 = sqd4(it.rl, it.w2, 0.f); d3 = sqd4(it.rl, it.w3, 0.f); }
-    else { d0 = dot4(it.rl, it.w0, 0.f); d1 = dot4(it.rl, it.w1, 0.f); d2 = dot4(it.rl, it.w2, 0.f); d3 = dot4(it.rl, it.w3, 0.f); }
+    const int j = lane & 7;
+    float rr = (dot4(it.rl[0], it.rl[0], 0.f) + dot4(it.rl[1], it.rl[1], 0.f)) + (dot4(it.rl[2], it.rl[2], 0.f) + dot4(it.rl[3], it.rl[3], 0.f));
+    float d = direct ? (sqd4(it.rl[0], it.w[0], 0.f) + sqd4(it.rl[1], it.w[1], 0.f)) + (sqd4(it.rl[2], it.w[2], 0.f) + sqd4(it.rl[3], it.w[3], 0.f))
+                     : (dot4(it.rl[0], it.w[0], 0.f) + dot4(it.rl[1], it.w[1], 0.f)) + (dot4(it.rl[2], it.w[2], 0.f) + dot4(it.rl[3], it.w[3], 0.f));
     #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
+    for (int off = 4; off > 0; off >>= 1) {
       rr += __shfl_xor_sync(0xffffffffu, rr, off);
-      d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
-      d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
+      d += __shfl_xor_sync(0xffffffffu, d, off);
     }
-    float best = inf_f(); int bcode = 0x7fffffff; float4 wsel = it.w0;     // NaN distances only: the first candidate
-    auto consider = [&](float d, float nrm, int code, const float4& w) {
-      const float e = direct ? d : (rr - 2.f * d) + nrm;
-      if (code >= 0 && (e < best || (e == best && code < bcode))) { best = e; bcode = code; wsel = w; }
-    };
-    consider(d0, it.n0, it.cd.x, it.w0); consider(d1, it.n1, it.cd.y, it.w1);
-    consider(d2, it.n2, it.cd.z, it.w2); consider(d3, it.n3, it.cd.w, it.w3);
-    if (bcode == 0x7fffffff) bcode = it.cd.x;
-    *reinterpret_cast<float4*>(it.rp) = sub_row<TRAIN>(p, it.rl, wsel);
+    // exact fp32 distance of this quarter's candidate (core_vq.py:183-187; :86-88 for k-means), then the best of the four,
+    // lowest code on ties
+    float best = direct ? d : (rr - 2.f * d) + it.nrm;
+    int bcode = it.ck;
+    if (it.ck < 0 || !(best == best)) { best = inf_f(); bcode = 0x7fffffff; }
+    #pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oc = __shfl_xor_sync(0xffffffffu, bcode, off);
+      if (ob < best || (ob == best && oc < bcode)) { best = ob; bcode = oc; }
+    }
+    if (bcode == 0x7fffffff) bcode = it.cd.x;                   // NaN distances only: the first candidate
+    if (it.ck == bcode) {                                        // the winner's quarter holds its row: r <- r - q
+      #pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(rs + rs_off(it.f, 8 * k + j)) = sub_row<TRAIN>(p, it.rl[k], it.w[k]);
+    }
     const int64_t nfr = tile_n0 + it.f;
     if (lane == 0) {
       *reinterpret_cast<int*>(ms + Sm::m_cand + it.f * 16) = bcode;

@@ -54,6 +54,30 @@ __global__ void __launch_bounds__(320, 1) gather_kernel(const float* tab, const 
         for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
         #pragma unroll
         for (int i = 0; i < 8; ++i) acc += qa[i].x + qb[i].y + qa[i].z + qb[i].w;
+      } else if (MODE == 3) {
+        const int g = lane >> 2, m = lane & 3;
+        const int fA = warp * 16 + g, fB = fA + 8;
+        const float4* ra = reinterpret_cast<const float4*>(tab + size_t(codes[fA]) * 128) + 2 * m;
+        const float4* rb = reinterpret_cast<const float4*>(tab + size_t(codes[fB]) * 128) + 2 * m;
+        float4 qa[8], qb[8];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) { qa[2 * j] = __ldg(ra + 8 * j); qa[2 * j + 1] = __ldg(ra + 8 * j + 1); }
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) { qb[2 * j] = __ldg(rb + 8 * j); qb[2 * j + 1] = __ldg(rb + 8 * j + 1); }
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) acc += qa[i].x + qb[i].y + qa[i].z + qb[i].w;
+      } else if (MODE == 4) {
+        // 8 lanes per row, 2 rows per lane group of 8: lane j of the octet loads chunks 8k + j (a full 128 B line per instruction)
+        const int o = lane >> 3, j = lane & 7;
+        float4 q[16];
+        #pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4* rp = reinterpret_cast<const float4*>(tab + size_t(codes[warp * 16 + 4 * r + o]) * 128) + j;
+          #pragma unroll
+          for (int k = 0; k < 4; ++k) q[4 * r + k] = __ldg(rp + 8 * k);
+        }
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) acc += q[i].x + q[i].w;
       } else if (MODE == 1) {
         if (lane < 16) {
           const int f = warp * 16 + lane;
@@ -95,7 +119,11 @@ int main() {
     run<0, false>("LDG.128 x16 (registers)", tab, img, out, sink);
     run<1, false>("bulk 512 B x128 (TMA -> smem)", tab, img, out, sink);
     run<2, false>("LDGSTS 16 B (cp.async -> smem)", tab, img, out, sink);
+    run<3, false>("LDG.128 x16, 32 B per lane", tab, img, out, sink);
+    run<4, false>("LDG.128 x16, 8 lanes per row (full lines)", tab, img, out, sink);
     run<0, true>("LDG.128 x16 + codebook stream", tab, img, out, sink);
+    run<3, true>("LDG.128 x16, 32 B per lane + stream", tab, img, out, sink);
+    run<4, true>("LDG.128 x16, 8 lanes per row + stream", tab, img, out, sink);
     run<1, true>("bulk 512 B x128 + codebook stream", tab, img, out, sink);
     run<2, true>("LDGSTS 16 B + codebook stream", tab, img, out, sink);
   }
