@@ -127,10 +127,16 @@ def segmented(name, b, t_total, seg, n_q, fr, bw, dev, reps, out):
     q = quantizer(n_q, dev).eval()
     x = latents(b, t_total, 5, dev)
     segs = [x[:, :, o:o + seg] for o in range(0, t_total, seg)]
+    # the segments as separate tensors (each one comes out of its own SEANet call in model.py:141-145)
+    segs = [s.contiguous() for s in segs]
     with torch.no_grad():
         ms = timed(lambda i: [q.encode(s, fr, bw) for s in segs], reps)
+        ms_batched = timed(lambda i: q.encode_segments(segs, fr, bw), reps)
+        same = all(torch.equal(a, c) for a, c in zip(q.encode_segments(segs, fr, bw), [q.encode(s, fr, bw) for s in segs]))
     out[name] = {"shape": [b, D, t_total], "segment_frames": seg, "calls": len(segs), "n_q": n_q,
-                 "encode_ms_all_segments": ms, "encode_frames_per_s": b * t_total / ms * 1e3}
+                 "encode_ms_all_segments": ms, "encode_frames_per_s": b * t_total / ms * 1e3,
+                 "encode_segments_ms": ms_batched, "encode_segments_frames_per_s": b * t_total / ms_batched * 1e3,
+                 "encode_segments_equal_to_loop": bool(same)}
     print(name, json.dumps(out[name]), flush=True)
 
 
