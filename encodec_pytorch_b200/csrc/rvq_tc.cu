@@ -412,18 +412,10 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     // processing order).  Straight-line for the usual case of at most two flagged batches and classes (the first candidate
     // is always (lowest batch, lowest class), the order of the others does not matter: ties go to the lowest CODE);
     // three or four flagged classes of one batch (or vice versa) take the generic walk.
+    it.cd = cand[it.f];                       // the score warp left all codes of a short list
+    if (it.cd.y != -2) return;
     const uint32_t cmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + it.f * 4);
     const uint32_t bmk = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + it.f * 4);
-    const int nc = __popc(cmk), nb = __popc(bmk);
-    if (nc <= 2 && nb <= 2) {
-      const int b0 = __ffs(bmk) - 1, b1 = 31 - __clz(bmk), c0 = __ffs(cmk) - 1, c1 = 31 - __clz(cmk);
-      const bool two = nc == 2 && nb == 2;
-      it.cd.x = code_of(b0, c0, rot, nchunks);
-      it.cd.y = nc == 2 ? code_of(b0, c1, rot, nchunks) : code_of(b1, c0, rot, nchunks);
-      it.cd.z = two ? code_of(b1, c0, rot, nchunks) : -1;
-      it.cd.w = two ? code_of(b1, c1, rot, nchunks) : -1;
-      return;
-    }
     it.cd = make_int4(-1, -1, -1, -1);
     uint32_t bm2 = bmk;
     int w = 0;
@@ -956,7 +948,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
 
         // first candidate (= the winner when certified); the update warps enumerate the other codes of a short list
         // from the two masks
-        const int4 cd = make_int4(code_of(__ffs(bmask) - 1, __ffs(cmask) - 1, rot, nchunks), -1, -1, -1);
+        // ... for the usual short list (at most two flagged batches and classes) all of its codes: the update warps then
+        // start from addresses instead of walking masks (y = -2: more than two of a kind, enumerate the masks)
+        int4 cd;
+        {
+          const int b0 = __ffs(bmask) - 1, b1 = 31 - __clz(bmask | 1u), c0 = __ffs(cmask) - 1, c1 = 31 - __clz(cmask | 1u);
+          const bool two = nc == 2 && nb == 2;
+          cd.x = code_of(b0, c0, rot, nchunks);
+          cd.y = (nc > 2 || nb > 2) ? -2 : (nc == 2 ? code_of(b0, c1, rot, nchunks) : code_of(b1, c0, rot, nchunks));
+          cd.z = two ? code_of(b1, c0, rot, nchunks) : -1;
+          cd.w = two ? code_of(b1, c1, rot, nchunks) : -1;
+        }
         *reinterpret_cast<int4*>(ms + Sm::m_cand + f * 16) = cd;
         *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
         *reinterpret_cast<uint32_t*>(ms + Sm::m_cmask + f * 4) = cmask;
