@@ -227,18 +227,6 @@ __device__ __forceinline__ void bulk_g2s_expect_w(uint32_t dst_smem, const void*
       "l"(src_gmem), "r"(bytes), "r"(bar)
       : "memory");
 }
-// experiment: the same copy twice (doubles the L2 -> SM traffic of the stream, same result)
-__device__ __forceinline__ void bulk_g2s_dup_w(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t.reg .b32 b2;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "shl.b32 b2, %2, 1;\n\t"
-      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], b2;\n\t"
-      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
-      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst_smem),
-      "l"(src_gmem), "r"(bytes), "r"(bar)
-      : "memory");
-}
 // all MMAs issued so far by this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

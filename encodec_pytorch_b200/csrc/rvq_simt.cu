@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     // score error of code k for a frame r with fp16 image r~ = r - dr, operand row b_k = fp16(-2 c_k) = -2 c_k - db_k:
     //   sum_d (r~_d b_kd + 2 r_d c_kd) = -r.db_k + 2 c_k.dr + dr.db_k   =>   |.| <= |r| dbmax + (2 cref + dbmax) |dr|
     const float dbmax = sqrtf(s_db2) * 1.0001f;
-    m.margin_coef = margin_scale * 2.f * kMarginSlack * dbmax;
+    // + the tensor core's fp32 accumulation of the 144 products of a score (|sum| <= |r~| |b_k| <= 2 |r| cref): an absolute
+    // term, so that operands which happen to be exact in fp16 (dbmax = 0, |dr| = 0) are still covered
+    m.margin_coef = margin_scale * (2.f * kMarginSlack * dbmax + 144.f * 1.1920929e-7f * 2.f * s_cref);
     m.margin_dr = margin_scale * 2.f * kMarginSlack * (2.f * s_cref + dbmax);
     // |c|^2 is carried as fp16 hi + fp16 lo: error <= 2^-22 |c|^2 (+ 2^-24 when lo is subnormal)
     m.margin_abs = 2.f * (2.4e-7f * s_cref * s_cref + 6e-8f);
