@@ -49,6 +49,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "rvq_kmeans_update": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "rvq_residual_combine": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "rvq_search_counters": (_i, [_vp]),
+    "rvq_pack_bound_mode": (_i, [_i]),
 }
 
 

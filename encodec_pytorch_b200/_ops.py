@@ -278,3 +278,20 @@ class search_counters:
     def read(self) -> tp.Dict[str, int]:
         vals = self.buf.cpu().tolist()
         return {n: int(vals[i]) for i, n in enumerate(self.NAMES)}
+
+
+class pack_bound_mode:
+    """Context manager: the score-error bound ``rvq_pack`` prepares the tcgen05 search with (``rvq_pack_bound_mode``):
+    0 = chosen per stage (default), 1 = per-code bound on every stage, 2 = per-stage bound on every stage.  Both bounds
+    are rigorous; packs built inside the block keep their mode (cached packs need ``invalidate()`` to be rebuilt)."""
+
+    def __init__(self, mode: int):
+        self.mode = int(mode)
+
+    def __enter__(self):
+        self.prev = L.load().rvq_pack_bound_mode(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        L.load().rvq_pack_bound_mode(self.prev)
+        return False

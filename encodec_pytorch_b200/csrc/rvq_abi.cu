@@ -24,6 +24,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 static thread_local unsigned long long* g_counters = nullptr;
 unsigned long long* search_counters() { return g_counters; }
 
+static std::atomic<int> g_bound_mode{0};
+int pack_bound_mode() { return g_bound_mode.load(std::memory_order_relaxed); }
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // The library is built for sm_100a only: refuse anything else loudly (no fallback of any kind).
@@ -58,6 +61,7 @@ using namespace rvq;
 extern "C" {
 
 int rvq_version(void) { return RVQ_ABI_VERSION; }
+int rvq_pack_bound_mode(int mode) { return g_bound_mode.exchange(mode < 0 || mode > 2 ? 0 : mode, std::memory_order_relaxed); }
 const char* rvq_last_error(void) { return g_err; }
 int rvq_device_ok(void) { return check_device(); }
 uint64_t rvq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

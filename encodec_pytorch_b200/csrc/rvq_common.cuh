@@ -22,6 +22,8 @@ namespace rvq {
 //                            shared-memory image of a 128-code x 144-K UMMA B operand
 //     meta    StageMeta
 //     outl    u8 [K]         1 = code excluded from the fp16 image (outlier norm / fp16 range)
+//     gab     float2 [K]     per-code score-error coefficients {g16 + a_k, b_k} (StageMeta::percode), then
+//             fp16 [K]       g16_k: the coefficient carried by the fp16 image (augmented columns 2 and 4)
 // ----------------------------------------------------------------------------------------------
 constexpr int kHeaderBytes  = 256;
 constexpr int kTcChunkCodes = 128;                 // codes per UMMA N tile
@@ -46,13 +48,22 @@ struct StageMeta {
   int   n_outliers;    // codes excluded from the fp16 image (provably non-winning under xlimit)
   float cmax_all;      // largest norm among ALL codes (bounds the residual growth of exact-path frames)
   float margin_dr;
+  // Per-code bound (tables whose code norms are heterogeneous, e.g. fitted ones: the codes that compete for a frame are
+  // the small ones, and the bound above is set by the largest).  With a_k = |fp16(-2c_k) + 2c_k| (+ accumulation) and
+  // b_k = 2|c_k| + that:   |S_k - s_k| <= a_k |r| + b_k |r - fp16(r)|,   |r - fp16(r)| <= 2^-11 |r| (+ subnormals).
+  // The image carries g16_k >= a_k + 2^-11 b_k in its augmented columns and the frame's operand an upper bound R of
+  // |r|, so the tensor core delivers the LOWER bounds T_k = S_k - g16_k R <= s_k directly; for ANY code k',
+  // s_winner <= s_k' <= T_k' + (g16_k' + a_k') R + b_k' |r - fp16(r)| + abs_pc: the threshold the candidates' T are held against.
+  int   percode;       // 1: the search uses the per-code bound for this stage
+  float abs_pc;        // absolute term of the per-code threshold
+  float g16max;        // largest g16_k (fallback threshold when the minimum of T is not unique)
 };
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 __host__ __device__ inline bool tc_shape(int K, int D) { return D == 128 && K >= kTcChunkCodes && K <= 1024 && (K % kTcChunkCodes) == 0; }
 
 struct StageLayout {
-  size_t off_tab32, off_tab32T, off_cnorm, off_tc, off_meta, off_outl, stride;
+  size_t off_tab32, off_tab32T, off_cnorm, off_tc, off_meta, off_outl, off_gab, stride;
 };
 __host__ __device__ inline StageLayout stage_layout(int K, int D) {
   StageLayout L;
@@ -63,6 +74,7 @@ __host__ __device__ inline StageLayout stage_layout(int K, int D) {
   L.off_tc = o;     o += tc_shape(K, D) ? size_t(K / kTcChunkCodes) * kTcChunkBytes : 0;
   L.off_meta = o;   o += 256;
   L.off_outl = o;   o += tc_shape(K, D) ? align256(size_t(K)) : 0;      // u8 [K]: codes excluded from the fp16 image
+  L.off_gab = o;    o += tc_shape(K, D) ? align256(size_t(K) * 10) : 0; // float2 [K] {g16 + a, b}, then fp16 [K] g16
   L.stride = o;
   return L;
 }
@@ -78,6 +90,8 @@ struct PackView {
   __host__ __device__ const unsigned char* tc(int s) const { return stage(s) + L.off_tc; }
   __host__ __device__ const StageMeta* meta(int s) const { return (const StageMeta*)(stage(s) + L.off_meta); }
   __host__ __device__ const unsigned char* outl(int s) const { return stage(s) + L.off_outl; }
+  __host__ __device__ const float2* gab(int s) const { return (const float2*)(stage(s) + L.off_gab); }
+  __host__ __device__ const __half* g16(int s, int K) const { return (const __half*)(stage(s) + L.off_gab + size_t(K) * 8); }
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -129,6 +143,8 @@ __device__ __forceinline__ int64_t code_index(int bkt, int n_q, int T, int64_t N
 
 // optional search counters of the calling thread (rvq_search_counters); nullptr = off
 unsigned long long* search_counters();
+// rvq_pack_bound_mode: 0 = per stage (heterogeneous norms -> per-code bound), 1 = per-code everywhere, 2 = per-stage everywhere
+int pack_bound_mode();
 
 // ---- entry points implemented per translation unit -------------------------------------------
 struct EncodeArgs {

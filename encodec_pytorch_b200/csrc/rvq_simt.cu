@@ -50,7 +50,7 @@ constexpr float kOutlierMul = 64.f;                  // codes with |c| > 64 * (1
 constexpr float kBigScore   = 60000.f;               // fp16-representable score of an outlier code
 constexpr float kHalfSafe   = 3.0e4f;                // |2c| elements and |c|^2 must stay below fp16 max
 
-__global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, int stage_base, int K, int D, float margin_scale) {
+__global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, int stage_base, int K, int D, float margin_scale, int bound_mode) {
   extern __shared__ float sh[];          // [Kpow2] sorted norms, then [K] flags
   const int s = stage_base + blockIdx.x;
   PackView pv(pack, K, D);
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       __syncthreads();
     }
   }
-  __shared__ float s_thr, s_cref, s_cmin, s_outmin, s_cmax, s_db2;
+  __shared__ float s_thr, s_cref, s_cmin, s_outmin, s_cmax, s_db2, s_gmax, s_bmax, s_nlow;
   __shared__ int s_nout;
   if (threadIdx.x == 0) {
     // reference norm for the outlier test: a high quantile (15/16), not the median -- a codebook whose norms are bimodal
@@ -104,16 +104,21 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     s_thr = kOutlierMul * ref;
     s_cmin = norms[0];
     s_cmax = norms[K - 1];
-    s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0; s_db2 = 0.f;
+    s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0; s_db2 = 0.f; s_gmax = 0.f; s_bmax = 0.f;
+    s_nlow = norms[K / 64];                // a low quantile of the norms (the K/64 smallest codes are at or below it)
   }
   __syncthreads();
   // classify (a code is an outlier by norm ratio or by fp16 range); reduce cref / min outlier norm
   {
-    float lcref = 0.f, loutmin = __int_as_float(0x7f800000), ldb2 = 0.f; int lnout = 0;
+    float lcref = 0.f, loutmin = __int_as_float(0x7f800000), ldb2 = 0.f, lgmax = 0.f, lbmax = 0.f; int lnout = 0;
+    float2* gab = const_cast<float2*>(pv.gab(s));
+    __half* g16 = const_cast<__half*>(pv.g16(s, K));
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       float nv = sqrtf(cn[k]);
       bool o = outl[k] || !(nv <= s_thr);
       outl[k] = o ? 1 : 0;
+      float2 ab = make_float2(0.f, 0.f);
+      __half gh = __float2half_rn(0.f);
       if (o) { loutmin = fminf(loutmin, nv); ++lnout; }
       else {
         lcref = fmaxf(lcref, nv);
@@ -122,10 +127,24 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
         float e2 = 0.f;
         for (int d = 0; d < D; ++d) { const float b = -2.f * col[size_t(d) * K]; const float e = b - __half2float(__float2half_rn(b)); e2 = fmaf(e, e, e2); }
         ldb2 = fmaxf(ldb2, e2);
+        // per-code coefficients (StageMeta): |S_k - s_k| <= a_k |r| + b_k |r - fp16(r)|; the image carries
+        // g16_k >= a_k + 2^-11 b_k (rounded UP to fp16, so that S_k - g16_k R stays a lower bound of s_k)
+        const float nvu = nv * 1.0001f;
+        const float dbk = sqrtf(e2) * 1.0001f;
+        const float ak = margin_scale * (kMarginSlack * dbk + 144.f * 1.1920929e-7f * 2.f * nvu);
+        const float bk = margin_scale * kMarginSlack * (2.f * nvu + dbk);
+        // (at least the smallest normal fp16: nothing then depends on how the tensor core treats subnormal operands)
+        gh = __float2half_ru(fmaxf((ak + bk * kHalfUlp * 1.001f) * 1.00001f, 6.2e-5f));
+        const float g = __half2float(gh);
+        ab = make_float2((g + ak) * 1.00001f, bk);
+        lgmax = fmaxf(lgmax, g); lbmax = fmaxf(lbmax, bk);
       }
+      gab[k] = ab; g16[k] = gh;
     }
     atomicMax((int*)&s_cref, __float_as_int(lcref));          // non-negative floats order as ints
     atomicMax((int*)&s_db2, __float_as_int(ldb2));
+    atomicMax((int*)&s_gmax, __float_as_int(lgmax));
+    atomicMax((int*)&s_bmax, __float_as_int(lbmax));
     atomicMin((int*)&s_outmin, __float_as_int(loutmin));
     atomicAdd(&s_nout, lnout);
   }
@@ -143,6 +162,13 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     m.margin_dr = margin_scale * 2.f * kMarginSlack * (2.f * s_cref + dbmax);
     // |c|^2 is carried as fp16 hi + fp16 lo: error <= 2^-22 |c|^2 (+ 2^-24 when lo is subnormal)
     m.margin_abs = 2.f * (2.4e-7f * s_cref * s_cref + 6e-8f);
+    // per-code bound: worth its extra look-up when a group of codes is well below the largest one, which sets the per-stage
+    // bound (fitted tables: the codes that compete for typical frames are the small, populous ones -- measured on B200 at
+    // cfg2: 2.27 -> 0.53 ms on a fitted stack, 0.52 -> 0.56 ms on uniform norms).  + the part of |r - fp16(r)| that fp16
+    // subnormals add to the relative bound 2^-11 |r| (sqrt(128) 2^-25) times the largest b_k.
+    m.percode = bound_mode == 1 ? 1 : bound_mode == 2 ? 0 : (s_cref > 1.5f * s_nlow ? 1 : 0);
+    m.abs_pc = m.margin_abs + s_bmax * 3.5e-7f + s_gmax * 6.2e-5f;      // (last term: a frame bound R below the normal fp16 range)
+    m.g16max = s_gmax;
     // |x| bound under which (a) outlier codes provably lose to the smallest-norm code and
     // (b) every live score + margin stays below the outlier score, (c) x fits fp16.
     float xl = 6.0e4f;
@@ -186,6 +212,8 @@ __global__ void __launch_bounds__(256) pack_image_kernel(unsigned char* pack, in
       h[0] = hi; h[1] = lo;
       #pragma unroll
       for (int j = 2; j < 8; ++j) h[j] = __float2half_rn(0.f);
+      // columns 2 and 4: -g16_k, met by the frame's bound(s) of |r| in the operand's augmented block (rvq_tc.cu)
+      h[2] = h[4] = __hneg(pv.g16(s, K)[k]);
     } else {
       #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(0.f);
@@ -209,7 +237,7 @@ int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* 
     dim3 grid((D + 31) / 32, (K + 31) / 32, ns), block(32, 8);
     pack_copy_kernel<<<grid, block, 0, st>>>(tab, (unsigned char*)pack, s0, K, D);
     RVQ_LAUNCH_CHECK("pack_copy_kernel");
-    pack_meta_kernel<<<ns, 1024, meta_smem, st>>>((unsigned char*)pack, s0, K, D, margin_scale);
+    pack_meta_kernel<<<ns, 1024, meta_smem, st>>>((unsigned char*)pack, s0, K, D, margin_scale, pack_bound_mode());
     RVQ_LAUNCH_CHECK("pack_meta_kernel");
     if (tc_shape(K, D)) {
       pack_image_kernel<<<dim3(ns, kTcKPad / 8), 256, 0, st>>>((unsigned char*)pack, s0, K, D);

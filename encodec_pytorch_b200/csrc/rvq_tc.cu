@@ -54,13 +54,16 @@ constexpr int kFull = 6;                // ncnt marker: exact scan of the whole 
 constexpr int kRsBytes = kM * 128 * 4;  // fp32 residual of one tile
 
 struct Sm {
-  static constexpr uint32_t aug = 0;                               // [2 k-groups][128 rows][16 B], no swizzle
-  static constexpr uint32_t ring = aug + 4096;
+  // augmented K block of the A operand (K-step 8), no swizzle: k-group 0 of slot 0, k-group 0 of slot 1 (per frame:
+  // 1, 1, R0, 0, R1, 0, 0, 0 -- the ones meet the hi/lo halves of |c|^2, R0 + R1 >= |r| meets -g16_k when the stage uses
+  // the per-code bound), then the all-zero k-group 1 shared by both slots
+  static constexpr uint32_t aug = 0;
+  static constexpr uint32_t ring = aug + 6144;
   static constexpr uint32_t rs = ring + kRing * kSlotBytes;        // 2 x fp32 [128 f][128 d], chunk-swizzled
   static constexpr uint32_t misc = rs + 2 * kRsBytes;              // 2 x per-slot block (offsets m_*)
   static constexpr uint32_t m_cand = 0;                            // int4 [128]: candidate codes (-1 = none)
-  static constexpr uint32_t m_ncnt = m_cand + kM * 16;             // int [128]
-  static constexpr uint32_t m_cmask = m_ncnt + kM * 4;             // u32 [128] flagged classes   (a fresh tile: |x|^2 of dims 0..63)
+  static constexpr uint32_t m_ncnt = m_cand + kM * 16;             // u8 [128]
+  static constexpr uint32_t m_cmask = m_ncnt + kM;                 // u32 [128] flagged classes   (a fresh tile: |x|^2 of dims 0..63)
   static constexpr uint32_t m_bmask = m_cmask + kM * 4;            // u32 [128] flagged batches   (a fresh tile: |x|^2 of dims 64..127)
   static constexpr uint32_t m_dr2 = m_bmask + kM * 4;              // float [2][128]: |r - fp16(r)|^2 of the current operand, per half of the dims
   static constexpr uint32_t m_slowq = m_dr2 + 2 * kM * 4;          // u8 [128]: frames with 2..4 listed candidates
@@ -68,13 +71,13 @@ struct Sm {
   static constexpr uint32_t m_qcnt = m_wideq + kM;                 // int [2]: queue lengths {slow, wide}
   static constexpr uint32_t m_size = m_qcnt + 16;
   static constexpr uint32_t bars = misc + 2 * m_size;
-  static constexpr uint32_t total = bars + 256;
+  static constexpr uint32_t total = bars + 224;
 };
 struct Bars {
   uint64_t full[kRing], empty[kRing], acc_full[kAccBufs], acc_empty[kAccBufs], a_ready[2], cand_ready[2], dr_ready[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 256, "barrier block");
+static_assert(sizeof(Bars) <= 224, "barrier block");
 // shared-window address of a barrier, from the CTA's window base (no generic->shared conversion inside the hot loops)
 #define RVQ_BAR(field, i) (sbase + Sm::bars + uint32_t(offsetof(Bars, field)) + 8u * uint32_t(i))
 static_assert(Sm::total <= 227 * 1024, "shared memory budget");
@@ -240,7 +243,7 @@ __device__ __forceinline__ void resolve_full(const float* rs, unsigned char* ms,
   if (lane == 0) {
     const int code = bcode == 0x7fffffff ? 0 : bcode;
     *reinterpret_cast<int4*>(ms + Sm::m_cand + f * 16) = make_int4(code, -1, -1, -1);
-    *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = 1;
+    ms[Sm::m_ncnt + f] = 1;
     if (code_out != nullptr) *code_out = code;
   }
   __syncwarp();
@@ -392,7 +395,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   const int* qc = reinterpret_cast<const int*>(ms + Sm::m_qcnt);
   const int nslow = qc[0], nwide = qc[1];
   const int4* cand = reinterpret_cast<const int4*>(ms + Sm::m_cand);
-  const int* ncnt = reinterpret_cast<const int*>(ms + Sm::m_ncnt);
+  const unsigned char* ncnt = ms + Sm::m_ncnt;
   const int g = lane >> 2, m = lane & 3;
   const int fA = q * 32 + h * 16 + g, fB = fA + 8;
   // The winner rows of the certified frames are requested FIRST: they are in flight while the listed frames are resolved.
@@ -607,9 +610,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     int* qc = reinterpret_cast<int*>(smem + Sm::misc + threadIdx.x * Sm::m_size + Sm::m_qcnt);
     qc[0] = 0; qc[1] = 0;
   }
-  // constant augmented K block of A: k-group 0 = (1, 1, 0, ...) picks up hi/lo of |c|^2, k-group 1 = 0
-  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
-    *reinterpret_cast<uint4*>(smem + Sm::aug + i * 16) = make_uint4(i < 128 ? pack_half2(1.f, 1.f) : 0u, 0u, 0u, 0u);
+  // augmented K block of A: k-group 0 of each slot = (1, 1, 0, ...) picks up hi/lo of |c|^2 (the per-frame bounds of |r|
+  // are written per stage), k-group 1 = 0
+  for (int i = threadIdx.x; i < 6144 / 16; i += blockDim.x)
+    *reinterpret_cast<uint4*>(smem + Sm::aug + i * 16) = make_uint4(i < 256 ? pack_half2(1.f, 1.f) : 0u, 0u, 0u, 0u);
   if (warp == 13) {
     ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
     ptx::tmem_relinquish();
@@ -620,10 +624,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 #ifdef RVQ_TC_TRACE
-  __shared__ long long s_t0;
-  if (threadIdx.x == 0) s_t0 = clock64();
+  long long* s_t0 = reinterpret_cast<long long*>(smem + Sm::bars + 216);      // padding of the barrier block
+  if (threadIdx.x == 0) *s_t0 = clock64();
   __syncthreads();
-  const long long t_kernel0 = s_t0;
+  const long long t_kernel0 = *s_t0;
 #endif
 
   if (warp >= 12) {
@@ -663,7 +667,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       // lane issues), so the operands of tcgen05.mma stay in uniform registers and a chunk costs a few dozen instructions. =====
       constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
       const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem);      // a provably warp-uniform copy (uniform register)
-      const uint64_t ad_aug = ptx::umma_desc_kmajor_noswz(sb + Sm::aug, 2048, 128);
+      // slot 0: k-group 0 at +0, slot 1: at +2048; the shared zero k-group 1 at +4096 (LBO 4096 / 2048)
+      const uint64_t ad_aug0 = ptx::umma_desc_kmajor_noswz(sb + Sm::aug, 4096, 128);
+      const uint64_t ad_aug1 = ptx::umma_desc_kmajor_noswz(sb + Sm::aug + 2048, 2048, 128);
       const uint64_t bd0 = ptx::umma_desc_kmajor_noswz(sb + Sm::ring, kTcLBO, kTcSBO);
       const uint32_t bar_full0 = sb + Sm::bars + uint32_t(offsetof(Bars, full));
       const uint32_t bar_empty0 = sb + Sm::bars + uint32_t(offsetof(Bars, empty));
@@ -679,6 +685,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           ptx::tc_fence_after();
           RVQ_TRACE(X, n, 0, lane == 0);
           const uint32_t a_tmem = tmem_u + kTmemA + 64 * X;
+          const uint64_t ad_aug = X ? ad_aug1 : ad_aug0;
           #pragma unroll 1
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t d_tmem = tmem_u + ab * kN;
@@ -722,6 +729,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + 32 + lane) * p.fa.sxd));
       }
     };
+    const int pc_first = __ldg(&pv.meta(p.stage0)->percode);
     auto load_tile = [&](int X, int tile) {
       float* rs = reinterpret_cast<float*>(smem + Sm::rs + X * kRsBytes);
       unsigned char* ms = smem + Sm::misc + X * Sm::m_size;
@@ -753,6 +761,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
       // |x|^2 of this half of the dims goes where the (not yet written) class / batch masks of the tile's first stage live
       reinterpret_cast<float*>(ms + (h ? Sm::m_bmask : Sm::m_cmask))[f] = xsum;
       reinterpret_cast<float*>(ms + Sm::m_dr2)[h * kM + f] = e2;
+      // per-code bound: this half's |x| (rounded up to fp16) goes to column 2 + 2h of the frame's augmented operand row;
+      // the two halves meet -g16_k in columns 2 and 4 of the image, and sqrt(a) + sqrt(b) >= sqrt(a + b) = |x|
+      *reinterpret_cast<uint32_t*>(smem + Sm::aug + X * 2048 + f * 16 + 4 + 4 * h) =
+          pc_first ? uint32_t(__half_as_ushort(__float2half_ru(sqrtf(xsum) * 1.0001f))) : 0u;
+      ptx::fence_proxy_async_smem();
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -858,6 +871,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         // margin coefficients of this stage: requested before the chunk loop, used after it
         const float mt_coef = __ldg(&meta->margin_coef), mt_abs = __ldg(&meta->margin_abs), mt_xlimit = __ldg(&meta->xlimit);
         const float mt_cmax = __ldg(&meta->cmax_all), mt_dr = __ldg(&meta->margin_dr);
+        // per-code bound (StageMeta): this stage's switch and constants, the next stage's switch (its operand's bound of
+        // |r| is written at the end of this one)
+        const int pc = __ldg(&meta->percode);
+        const int pc_next = s + 1 < p.n_q ? __ldg(&pv.meta(st + 1)->percode) : 0;
+        const float mt_abs_pc = __ldg(&meta->abs_pc), mt_g16max = __ldg(&meta->g16max);
+        const float2* gab = pv.gab(st);
         RVQ_TICK0();
         // ---- scores: per-class and per-batch minima of the K approximate scores of this frame ----
         float cm[32], bmin[32];
@@ -932,7 +951,27 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           m4[j] = fminf(m4[j], cm[8 * j + 7]);
         }
         const float m = fminf(ptx::fmin3(m4[0], m4[1], m4[2]), m4[3]);
-        const float thr = m + delta;
+        float thr = m + delta;
+        if (pc) {
+          // Per-code bound: the accumulator holds the lower bounds T_k = S_k - g16_k R of the true scores.  For the code k'
+          // that attains the minimum of T (it must be the only one, else the per-stage bound serves):
+          //   s_winner <= s_k' <= T_k' + (g16_k' + a_k') R + b_k' |r - fp16(r)| + abs =: thr,
+          // and every code whose T exceeds thr is beaten by k'.
+          uint32_t ce4[4] = {0u, 0u, 0u, 0u}, be4[4] = {0u, 0u, 0u, 0u};
+          #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(ce4[j & 3]) : "f"(cm[j]), "f"(m), "r"(1u << j));
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(be4[j & 3]) : "f"(bmin[j]), "f"(m), "r"(1u << j));
+          }
+          const uint32_t ceq = (ce4[0] | ce4[1]) | (ce4[2] | ce4[3]);
+          const uint32_t beq = ((be4[0] | be4[1]) | (be4[2] | be4[3])) >> (32 - 4 * nchunks);
+          const bool uniq = __popc(ceq) == 1 && __popc(beq) == 1;
+          const float2 ab = __ldg(gab + (uniq ? code_of(__ffs(beq) - 1, __ffs(ceq) - 1, rot, nchunks) : 0));
+          const uint4 arow = *reinterpret_cast<const uint4*>(smem + Sm::aug + X * 2048 + f * 16);
+          const float Rm = __half2float(__ushort_as_half((unsigned short)(arow.y & 0xffffu))) +
+                           __half2float(__ushort_as_half((unsigned short)(arow.z & 0xffffu)));      // the R the tensor core multiplied with
+          thr = uniq ? fmaf(ab.x, Rm, fmaf(ab.y, drn, m + mt_abs_pc)) : m + fmaf(mt_g16max, Rm, delta);
+        }
         uint32_t cm4[4] = {0u, 0u, 0u, 0u}, bm4[4] = {0u, 0u, 0u, 0u};
         #pragma unroll
         for (int j = 0; j < 32; ++j) {                // two instructions per value: compare, predicated OR with an immediate
@@ -960,7 +999,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           cd.w = two ? code_of(b1, c1, rot, nchunks) : -1;
         }
         *reinterpret_cast<int4*>(ms + Sm::m_cand + f * 16) = cd;
-        *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
+        ms[Sm::m_ncnt + f] = (unsigned char)(full ? kFull : (ncand > 4 ? kBig : ncand));
         *reinterpret_cast<uint32_t*>(ms + Sm::m_cmask + f * 4) = cmask;
         *reinterpret_cast<uint32_t*>(ms + Sm::m_bmask + f * 4) = bmask;
         int64_t* code_out = (f < p.tf && nfr < p.N) ? p.codes + code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr) : nullptr;
@@ -983,8 +1022,16 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         // upper bound of the next residual's |r|^2 (only the margin and the validity test use it):
         // the winner's approximate score is <= m + delta and off by <= delta/2
         if (full) { const float g2 = xnorm + mt_cmax; xx = g2 * g2; }
+        else if (pc) xx = fmaxf(xx + thr, 0.f) * 1.00001f + 1e-30f;      // thr bounds the winner's true score
         else xx = fmaxf(xx + m + 1.5f * delta, 0.f) * 1.00001f + 1e-30f;
         if (X) xx_1 = xx; else xx_0 = xx;
+        if (s + 1 < p.n_q) {
+          // the next stage's augmented operand row: (1, 1, R, 0, 0, 0, 0, 0), R >= |r| rounded up to fp16 (0 switches the
+          // per-code term off).  All MMAs of this stage have completed (their scores were consumed above).
+          const uint32_t rw = pc_next ? uint32_t(__half_as_ushort(__float2half_ru(sqrtf(xx) * 1.0001f))) : 0u;
+          *reinterpret_cast<uint4*>(smem + Sm::aug + X * 2048 + f * 16) = make_uint4(pack_half2(1.f, 1.f), rw, 0u, 0u);
+          ptx::fence_proxy_async_smem();
+        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(RVQ_BAR(cand_ready, X));    // winners and queues visible to the update warps
         RVQ_TRACE(X, n, 5, warp == 0 && lane == 0);

@@ -177,6 +177,15 @@ int rvq_residual_combine(const void* pack, int K, int D,
  * and reads the buffer.                                                                               */
 int rvq_search_counters(uint64_t* counters_dev);
 
+/* ---- which score-error bound the tcgen05 search certifies winners with (StageMeta in the pack; core_vq.py:181-189 is the
+ * arithmetic being certified).  Both bounds are rigorous -- the choice changes how many frames take the exact fp32
+ * re-score, never a result:
+ *   0 (default) per stage at rvq_pack time: the per-code bound where the code norms are heterogeneous (fitted tables),
+ *               the per-stage bound where they are uniform (freshly initialised tables);
+ *   1 per-code bound on every stage;   2 per-stage bound on every stage.
+ * Process-wide; read by rvq_pack.  Returns the previous mode.                                             */
+int rvq_pack_bound_mode(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,12 +120,31 @@ def test_cfg2_trained_like_stack():
     q.eval()
     states = module_states(q)
     x = C.latents(64, 128, 750, 900)
-    with torch.no_grad():
-        codes = q.encode(x.cuda(), 75, 24.0)
-    st = O.compare_codes_teacher_forced(states, x, codes.cpu())
-    assert st["bad"] == 0 and st["near_tie"] <= 2e-3 * st["pairs"], st
+    # the three settings of the score-error bound (rvq_pack_bound_mode): per-stage everywhere, per-code everywhere, chosen
+    # per stage.  All must produce the oracle's codes; on fitted tables the per-code bound certifies far more frames.
+    from encodec_pytorch_b200 import _ops as ops
+    share = {}
+    for mode in (2, 1, 0):
+        with ops.pack_bound_mode(mode):
+            q.vq.invalidate()
+            with ops.search_counters(torch.device("cuda", 0)) as counters, torch.no_grad():
+                codes = q.encode(x.cuda(), 75, 24.0)
+        c = counters.read()
+        share[mode] = c["certified"] / c["searched"]
+        st = O.compare_codes_teacher_forced(states, x, codes.cpu())
+        assert st["bad"] == 0 and st["near_tie"] <= 2e-3 * st["pairs"], (mode, st)
+    assert share[1] > share[2] + 0.03 and share[0] >= share[1] - 0.01, share
     with torch.no_grad():
         dec = q.decode(codes)
     assert torch.equal(dec.cpu(), O.rvq_decode(states, codes.cpu()))
     # the stack is really fitted: the residual after all stages is well below the input
     assert float((x - dec.cpu()).norm() / x.norm()) < 0.7
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_bound_modes_random_init(mode):
+    """Freshly initialised tables (uniform norms) under the per-code and the per-stage bound: same codes as the oracle."""
+    from encodec_pytorch_b200 import _ops as ops
+    case = C.Case(f"bound_mode{mode}", 16, 128, 750, 1024, 8, 75, None, 77, 0)
+    with ops.pack_bound_mode(mode):
+        _encode_decode_against_oracle(case)
