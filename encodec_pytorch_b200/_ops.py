@@ -277,7 +277,9 @@ class search_counters:
 
     def read(self) -> tp.Dict[str, int]:
         vals = self.buf.cpu().tolist()
-        return {n: int(vals[i]) for i, n in enumerate(self.NAMES)}
+        out = {n: int(vals[i]) for i, n in enumerate(self.NAMES)}
+        out["wide"], out["wide_candidates"] = int(vals[11]), int(vals[12])     # frames with more than 4 candidates, their total
+        return out
 
 
 class pack_bound_mode:

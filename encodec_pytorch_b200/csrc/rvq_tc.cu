@@ -177,7 +177,8 @@ __device__ __forceinline__ float residue_of(float a, float b, uint32_t word, flo
   return fmaf(eb, eb, fmaf(ea, ea, e2));
 }
 
-// tiles [start, start+cnt) of this CTA
+// tiles [start, start+cnt) of this CTA (contiguous ranges: measured 1 % faster at cfg2 than the interleaved order
+// blockIdx.x + j * gridDim.x, whose only merit is to spread a stretch of expensive frames over more CTAs)
 __device__ __forceinline__ void cta_range(int ntiles, int& start, int& cnt) {
   const int base = ntiles / int(gridDim.x), rem = ntiles % int(gridDim.x);
   const int b = blockIdx.x;
@@ -297,9 +298,9 @@ template <int NC> struct Cand { int c[NC]; Row4 w[NC]; float nrm[NC]; };
 template <int NC>
 __device__ __forceinline__ void load_cand(Cand<NC>& k, int j, const float* __restrict__ t32, const float* __restrict__ cn) {
   #pragma unroll
-  for (int u = 0; u < NC; ++u) {
-    k.nrm[u] = 0.f;
-    if (k.c[u] >= 0) { k.w[u] = load_row(t32, k.c[u], j); k.nrm[u] = __ldg(cn + k.c[u]); }
+  for (int u = 0; u < NC; ++u) {      // (unconditional: a conditionally initialised struct is kept in local memory)
+    const int c = k.c[u] < 0 ? 0 : k.c[u];
+    k.w[u] = load_row(t32, c, j); k.nrm[u] = __ldg(cn + c);
   }
 }
 // exact distances of up to NC candidates (core_vq.py:183-187); keeps the best (lowest code on ties) and its slot u
@@ -321,56 +322,48 @@ __device__ __forceinline__ void score_cand(const Cand<NC>& k, const Row4& r, flo
     if (k.c[u] >= 0 && (e < best || (e == best && k.c[u] < bcode))) { best = e; bcode = k.c[u]; bidx = u; }
   }
 }
+// A frame whose flagged batches x flagged classes give more than 4 candidates: ALL update warps work on it, two candidates per
+// quarter-warp and step (64 per step), exact fp32 distances (core_vq.py:183-187).  Every quarter folds its best into the
+// frame's 64-bit key {orderable distance, code} with a shared-memory atomicMin -- smallest distance, lowest code on ties; the
+// key lives in the upper half of the frame's candidate entry, which the score warp left at all ones -- and the winner is read
+// after the update warps' barrier.  (Degenerate tables -- hundreds of near-identical codes -- give candidate sets of several
+// hundred codes: one warp per frame, 8 candidates per step, took 100 k cycles for such a frame.)
 template <bool TRAIN>
-__device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs, unsigned char* ms, int f, int lane, int s, int rot, int nchunks,
-                                             int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn) {
+__device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs, unsigned char* ms, int f, int u, int lane, int rot, int nchunks,
+                                             const float* __restrict__ t32, const float* __restrict__ cn) {
   const int qq = lane >> 3, j = lane & 7;
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
   const uint32_t bm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + f * 4);
-  const int nc = __popc(cm);
+  const int nc = __popc(cm), total = nc * __popc(bm);
+  constexpr int kPer = 4;                                  // candidates per quarter-warp and step
+  if (4 * kPer * u >= total) return;                       // (warp-uniform) no candidate left for this warp
+  const int w = 4 * u + qq;                                // this quarter's number among the 32 of the update warps
+  // lane L: position of the L-th flagged batch / class (candidate t = flagged batch t / nc, flagged class t % nc)
+  uint32_t mb = bm, mc = cm;
+  for (int i = 0; i < lane; ++i) { mb &= mb - 1; mc &= mc - 1; }
+  const int posb = mb ? __ffs(mb) - 1 : 0, posc = mc ? __ffs(mc) - 1 : 0;
+  const float inv_nc = 1.f / float(nc);
   const Row4 r = load_res(rs, f, j);
   const float rr = quarter_sum(dot_row(r, r));
   float best = inf_f(); int bcode = 0x7fffffff, bidx = 0;
-  // quarter qq takes the flagged batches number qq, qq + 4, ...; within a batch the flagged classes two at a time
-  uint32_t bmq = bm;
-  for (int i = 0; i < qq; ++i) bmq &= bmq - 1;
-  const int nb = __popc(bm);
   #pragma unroll 1
-  for (int ob = 0; ob < nb; ob += 4) {
-    const int a = bmq ? __ffs(bmq) - 1 : -1;
+  for (int t0 = 0; t0 < total; t0 += 4 * kPer * kUpdWarps) {
+    Cand<kPer> k;
     #pragma unroll
-    for (int i = 0; i < 4; ++i) bmq &= bmq - 1;
-    uint32_t cmq = cm;
-    #pragma unroll 1
-    for (int oc = 0; oc < nc; oc += 2) {
-      Cand<2> k;
-      #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int jj = cmq ? __ffs(cmq) - 1 : -1;
-        cmq &= cmq - 1;
-        k.c[u] = (a >= 0 && jj >= 0) ? code_of(a, jj, rot, nchunks) : -1;
-      }
-      load_cand<2>(k, j, t32, cn);
-      score_cand<2>(k, r, rr, best, bcode, bidx, TRAIN && p.direct);
+    for (int v = 0; v < kPer; ++v) {
+      const int t = t0 + kPer * w + v;
+      const int ia = int((float(t) + 0.5f) * inv_nc);      // exact for t < 1024, nc <= 32
+      const int ic = t - ia * nc;
+      const int a = __shfl_sync(0xffffffffu, posb, ia & 31), jj = __shfl_sync(0xffffffffu, posc, ic & 31);
+      k.c[v] = t < total ? code_of(a, jj, rot, nchunks) : -1;
     }
+    load_cand<kPer>(k, j, t32, cn);
+    score_cand<kPer>(k, r, rr, best, bcode, bidx, TRAIN && p.direct);
   }
-  // best over the four quarters (candidate codes are distinct, so the winner's quarter is unique)
-  float wb = best; int wc = bcode;
-  #pragma unroll
-  for (int off = 8; off <= 16; off <<= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, wb, off);
-    const int oc = __shfl_xor_sync(0xffffffffu, wc, off);
-    if (ob < wb || (ob == wb && oc < wc)) { wb = ob; wc = oc; }
-  }
-  bool mine = bcode == wc;
-  if (wc == 0x7fffffff) {                                  // NaN distances only: lowest candidate, like an exact scan would
-    mine = qq == 0;
-    if (mine) bcode = code_of(__ffs(bm) - 1, __ffs(cm) - 1, rot, nchunks);
-  }
-  const int64_t nfr = tile_n0 + f;
-  if (mine && j == 0) {
-    *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;      // the frame now has a single (exact) winner
-    if (f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = bcode;
+  if (j == 0 && bcode != 0x7fffffff) {                     // (NaN distances never enter: the key then stays at all ones)
+    uint32_t b = __float_as_uint(best + 0.f);              // -0 -> +0; then the usual order-preserving map to unsigned
+    b ^= (b >> 31) ? 0xffffffffu : 0x80000000u;
+    atomicMin(reinterpret_cast<unsigned long long*>(ms + Sm::m_cand + f * 16 + 8), (static_cast<unsigned long long>(b) << 32) | uint32_t(bcode));
   }
 }
 
@@ -489,9 +482,9 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
       item_load(i, it0);
       item_finish(it0);
     }
-    // wide candidate sets: one frame per warp at a time, handed out from the last warp down
+    // wide candidate sets: one frame at a time, all warps together
     #pragma unroll 1
-    for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
+    for (int i = 0; i < nwide; ++i) resolve_wide<TRAIN>(p, rs, ms, wideq[i], u, lane, rot, nchunks, t32, cn);
     RVQ_TRACE3(trX, trn, u, 1);
   }
   float4 qa[8], qb[8];
@@ -507,13 +500,22 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     ptx::named_bar_sync(6, kUpdWarps * 32);      // listed frames are updated, wide frames have their winner
     RVQ_TRACE3(trX, trn, u, 2);
     if (nwide > 0 && __any_sync(0xffffffffu, nA == kBig || nB == kBig)) {
-      const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
-      const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
+      // winners of the wide sets: low word of the frame's key (all ones = NaN distances only: the first candidate, like an
+      // exact scan would answer); the group's first lane writes the code out
+      auto wide_winner = [&](int f) {
+        const int4 cd = cand[f];
+        const int code = cd.z == -1 ? cd.x : cd.z;
+        const int64_t nfr = tile_n0 + f;
+        if (m == 0 && f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = code;
+        return code;
+      };
       if (nA == kBig) {
+        const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(wide_winner(fA)) * 128) + m;
         #pragma unroll
         for (int i = 0; i < 8; ++i) qa[i] = __ldg(ra + 4 * i);
       }
       if (nB == kBig) {
+        const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(wide_winner(fB)) * 128) + m;
         #pragma unroll
         for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
       }
@@ -847,7 +849,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
     const int q = warp;                        // TMEM lane quadrant = frames 32q..32q+31 of a tile
     const int f = q * 32 + lane;
     const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);
-    uint32_t n_cert = 0, n_resc = 0, n_full = 0;                        // search statistics (rvq_search_stats)
+    uint32_t n_cert = 0, n_resc = 0, n_full = 0, n_wide = 0, n_widec = 0;   // search statistics (rvq_search_counters)
 #ifdef RVQ_TC_TIMERS
     uint32_t t_wait = 0, t_epi = 0, t_win = 0;
     const long long t_begin = clock64();
@@ -1019,6 +1021,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
           }
         }
         n_full += full ? 1u : 0u; n_cert += (!full && ncand == 1) ? 1u : 0u; n_resc += (!full && ncand > 1) ? 1u : 0u;
+        if (!full && ncand > 4) { n_wide += 1u; n_widec += uint32_t(ncand); }
         // upper bound of the next residual's |r|^2 (only the margin and the validity test use it):
         // the winner's approximate score is <= m + delta and off by <= delta/2
         if (full) { const float g2 = xnorm + mt_cmax; xx = g2 * g2; }
@@ -1045,10 +1048,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
         n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
         n_resc += __shfl_xor_sync(0xffffffffu, n_resc, off);
         n_full += __shfl_xor_sync(0xffffffffu, n_full, off);
+        n_wide += __shfl_xor_sync(0xffffffffu, n_wide, off);
+        n_widec += __shfl_xor_sync(0xffffffffu, n_widec, off);
       }
       if (lane == 0) {
         atomicAdd(&p.counters[0], (unsigned long long)(n_cert + n_resc + n_full)); atomicAdd(&p.counters[1], (unsigned long long)n_cert);
         atomicAdd(&p.counters[2], (unsigned long long)n_resc); atomicAdd(&p.counters[3], (unsigned long long)n_full);
+        atomicAdd(&p.counters[11], (unsigned long long)n_wide); atomicAdd(&p.counters[12], (unsigned long long)n_widec);
 #ifdef RVQ_TC_TIMERS
         atomicAdd(&p.counters[4], (unsigned long long)t_wait); atomicAdd(&p.counters[5], (unsigned long long)t_epi);
         atomicAdd(&p.counters[6], (unsigned long long)t_win);

@@ -172,7 +172,8 @@ int rvq_residual_combine(const void* pack, int K, int D,
 
 /* ---- debug / evidence: optional counters of the tcgen05 search.  Registers, for the CALLING THREAD, a device buffer of
  * 32 x uint64 that every later rvq_encode of this thread accumulates into (atomics on the encode's stream):
- *   [0] frame-stages searched, [1] certified unique, [2] re-scored (candidate list / wide set), [3] exact scans.
+ *   [0] frame-stages searched, [1] certified unique, [2] re-scored (candidate list / wide set), [3] exact scans,
+ *   [11] re-scored frame-stages with more than 4 candidates, [12] the total of their candidates.
  * NULL (the default) turns the counters off; the codebook pack is never written after rvq_pack.  The caller zeroes
  * and reads the buffer.                                                                               */
 int rvq_search_counters(uint64_t* counters_dev);

@@ -133,6 +133,41 @@ def test_ties_wide_candidate_sets_and_non_finite_frames():
     assert stats["searched"] >= case.b * case.t * case.n_q and stats["rescored"] > 60   # padded tile rows count too
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_degenerate_tables_hundreds_of_candidates(mode):
+    """Tables with a crowd of near-identical codes (what a table looks like after its k-means init under the reference's EMA:
+    hundreds of rows shrunk towards the origin): frames whose best score sits inside the crowd get candidate sets of
+    several hundred codes, which all update warps re-score together in exact fp32.  Also exact duplicates of the crowd
+    (ties -> lowest index, core_vq.py:188), under the per-code and the per-stage bound."""
+    from encodec_pytorch_b200 import _ops as ops
+    case = C.Case("crowd", 4, 128, 200, 1024, 4, 75, None, 909, 12)
+    with ops.pack_bound_mode(mode):
+        q = build_module(case).eval()
+        g = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for i, n_small in enumerate((400, 900, 64, 940)):
+                e = q.vq.layers[i]._codebook.embed
+                idx = torch.randperm(1024, generator=g)[:n_small]
+                e[idx.cuda()] = (1e-3 * torch.randn(n_small, 128, generator=g)).cuda()
+            e1 = q.vq.layers[1]._codebook.embed
+            e1[700:720] = e1[3]                               # exact duplicates inside the crowd's neighbourhood
+            e2 = q.vq.layers[2]._codebook.embed               # a tight crowd around a full-size code
+            tight = torch.randperm(1024, generator=g)[:300].cuda()
+            e2[tight] = e2[tight[0]] + (1e-6 * torch.randn(300, 128, generator=g)).cuda()
+        q.vq.invalidate()
+        states = module_states(q)
+        x = C.latents(case.b, case.d, case.t, case.x_seed)
+        x[1] *= 0.02                                          # quiet frames: every code of the crowd is a candidate
+        x[2, :, :50] = 0.0
+        x[3, :, :60] = 3.0 * states[2]["embed"][int(tight[0])][:, None] + 0.3 * x[3, :, :60]   # their stage-2 winner is in the tight crowd
+        with torch.no_grad(), ops.search_counters("cuda") as counters:
+            got = q.encode(x.cuda(), 75)
+    st = O.compare_codes_teacher_forced(states, x, got.cpu())
+    assert st["bad"] == 0 and st["near_tie"] <= 0.02 * st["pairs"], st
+    c = counters.read()
+    assert c["wide"] > 100 and c["wide_candidates"] > 30 * c["wide"], c
+
+
 def test_layout_and_edge_cases():
     case = C.Case("edge", 3, 128, 17, 1024, 8, 75, None, 77, 2)
     q = build_module(case).eval()
