@@ -34,6 +34,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "rvq_pack_bytes": (_sz, [_i, _i, _i]),
     "rvq_pack": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
     "rvq_encode": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rvq_encode_train": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rvq_decode": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "rvq_decode_ex": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp]),
     "rvq_ema_stats": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),

@@ -58,12 +58,14 @@ def _strides_bdt(x: torch.Tensor) -> tp.Tuple[int, int, int]:
 def encode(pk: CodebookPack, x: torch.Tensor, stage0: int, n_q: int, *,
            want_quantized: bool = False, want_sqerr: bool = False, want_residual: bool = False,
            quantized_accum: tp.Optional[torch.Tensor] = None, flags: int = 0,
-           codes_bkt: bool = False, out_bdt: bool = False):
+           codes_bkt: bool = False, out_bdt: bool = False, ema_stats_out: tp.Optional[torch.Tensor] = None):
     """Fused multi-stage search on ``x [B, D, T]`` (any strides).
 
     Returns ``(codes [n_q,B,T] int64, quantized [B,T,D] | None, sqerr [n_q] float64 | None,
     residual [B,T,D] | None)``.  ``codes_bkt``: the codes come as a contiguous ``[B, n_q, T]`` tensor (model.py:166's
-    layout) instead; ``out_bdt``: ``quantized`` comes as a contiguous ``[B, D, T]`` tensor."""
+    layout) instead; ``out_bdt``: ``quantized`` comes as a contiguous ``[B, D, T]`` tensor.  ``ema_stats_out``: a flat
+    fp32 buffer of ``n_q*K + n_q*K*D`` elements (``ema_stats_buffer``) that receives the EMA statistics of
+    core_vq.py:227-228 from the same launch (``rvq_encode_train``)."""
     lib = L.load()
     L.require_cuda_f32(x, "x")
     if x.dim() != 3 or x.shape[1] != pk.D:
@@ -89,10 +91,28 @@ def encode(pk: CodebookPack, x: torch.Tensor, stage0: int, n_q: int, *,
     residual = torch.empty((B, T, D), dtype=torch.float32, device=dev) if want_residual else None
     sb, sd, st = _strides_bdt(x)
     with _guard(dev):
-        L.check(lib.rvq_encode(pk.buf.data_ptr(), pk.K, pk.D, x.data_ptr(), sb, sd, st, B, T, stage0, n_q,
-                               codes.data_ptr(), L.ptr(quantized), L.ptr(residual), L.ptr(sqerr), flags,
-                               L.stream_ptr(dev)), "rvq_encode")
+        if ema_stats_out is not None:
+            _, counts, esum = ema_stats_views(ema_stats_out, n_q, pk.K, pk.D)
+            L.check(lib.rvq_encode_train(pk.buf.data_ptr(), pk.K, pk.D, x.data_ptr(), sb, sd, st, B, T, stage0, n_q,
+                                         codes.data_ptr(), L.ptr(quantized), L.ptr(residual), L.ptr(sqerr),
+                                         counts.data_ptr(), esum.data_ptr(), flags, L.stream_ptr(dev)), "rvq_encode_train")
+        else:
+            L.check(lib.rvq_encode(pk.buf.data_ptr(), pk.K, pk.D, x.data_ptr(), sb, sd, st, B, T, stage0, n_q,
+                                   codes.data_ptr(), L.ptr(quantized), L.ptr(residual), L.ptr(sqerr), flags,
+                                   L.stream_ptr(dev)), "rvq_encode")
     return codes, quantized, sqerr, residual
+
+
+def ema_stats_buffer(n_q: int, K: int, D: int, device) -> torch.Tensor:
+    """The flat fp32 buffer ``[n_q*K] counts || [n_q*K*D] embed_sum`` of the EMA statistics (one all-reduce covers it)."""
+    return torch.empty(n_q * K + n_q * K * D, dtype=torch.float32, device=device)
+
+
+def ema_stats_views(flat: torch.Tensor, n_q: int, K: int, D: int):
+    n_cnt, n_sum = n_q * K, n_q * K * D
+    if not (flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() >= n_cnt + n_sum):
+        raise RuntimeError("EMA statistics buffer: expected a contiguous CUDA fp32 tensor of n_q*K*(D+1) elements")
+    return flat, flat[:n_cnt].view(n_q, K), flat[n_cnt:n_cnt + n_sum].view(n_q, K, D)
 
 
 def decode(pk: CodebookPack, codes: torch.Tensor, out_bdt: bool = False) -> torch.Tensor:
@@ -126,10 +146,7 @@ def ema_stats(pk: CodebookPack, x: torch.Tensor, codes: torch.Tensor, stage0: in
     n_q, B, T = (int(v) for v in codes.shape)
     assert codes.is_contiguous() and codes.dtype == torch.int64
     K, D = pk.K, pk.D
-    n_cnt, n_sum = n_q * K, n_q * K * D
-    flat = out if out is not None else torch.empty(n_cnt + n_sum, dtype=torch.float32, device=x.device)
-    counts = flat[:n_cnt].view(n_q, K)
-    esum = flat[n_cnt:n_cnt + n_sum].view(n_q, K, D)
+    flat, counts, esum = ema_stats_views(out if out is not None else ema_stats_buffer(n_q, K, D, x.device), n_q, K, D)
     sb, sd, st = _strides_bdt(x)
     with _guard(x.device):
         L.check(lib.rvq_ema_stats(pk.buf.data_ptr(), K, D, x.data_ptr(), sb, sd, st, B, T, stage0, n_q,

@@ -99,6 +99,28 @@ int rvq_encode(const void* pack, int K, int D, const float* x, int64_t sxb, int6
   return want_tc ? tc_encode(a, st) : simt_encode(a, st);
 }
 
+int rvq_encode_train(const void* pack, int K, int D, const float* x, int64_t sxb, int64_t sxd, int64_t sxt,
+                     int B, int T, int stage0, int n_q, int64_t* codes, float* quantized, float* residual_out,
+                     double* stage_sqerr, float* counts, float* embed_sum, int flags, void* stream) {
+  if (int e = check_device()) return e;
+  RVQ_REQUIRE(pack && counts && embed_sum, "rvq_encode_train: null pointer");
+  RVQ_REQUIRE(B >= 0 && T >= 0 && n_q >= 0 && stage0 >= 0 && K > 0 && D > 0, "rvq_encode_train: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool want_tc = tc_shape(K, D) && !(flags & RVQ_FLAG_FORCE_EXACT);
+  if (!want_tc) {      // other shapes: the fp32 search, then the statistics pass over its codes
+    if (int e = rvq_encode(pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, residual_out, stage_sqerr, flags, stream)) return e;
+    return rvq_ema_stats(pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, counts, embed_sum, flags, stream);
+  }
+  RVQ_CUDA(cudaMemsetAsync(counts, 0, size_t(n_q) * K * 4, st));
+  RVQ_CUDA(cudaMemsetAsync(embed_sum, 0, size_t(n_q) * K * D * 4, st));
+  if (int64_t(B) * T == 0 || n_q == 0) return RVQ_OK;
+  RVQ_REQUIRE(x && codes, "rvq_encode_train: null pointer");
+  RVQ_REQUIRE(int64_t(B) * T < (int64_t(1) << 31), "rvq_encode_train: more than 2^31 frames in one call");
+  EncodeArgs a{pack, K, D, x, sxb, sxd, sxt, B, T, stage0, n_q, codes, quantized, residual_out, stage_sqerr, flags};
+  a.ema_counts = counts; a.ema_sum = embed_sum;
+  return tc_encode(a, st);
+}
+
 int rvq_kmeans_assign(const void* pack, int K, int D, const float* samples, int64_t N, int64_t* buckets, void* stream) {
   if (int e = check_device()) return e;
   RVQ_REQUIRE(pack && (N == 0 || (samples && buckets)), "rvq_kmeans_assign: null pointer");

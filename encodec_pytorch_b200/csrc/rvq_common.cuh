@@ -153,6 +153,7 @@ struct EncodeArgs {
   int stage0, n_q;
   int64_t* codes; float* quantized; float* residual_out; double* sqerr;
   int flags;
+  float* ema_counts = nullptr; float* ema_sum = nullptr;   // rvq_encode_train: EMA statistics accumulated by the search itself
 };
 int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st);
 int simt_encode(const EncodeArgs& a, cudaStream_t st);

@@ -118,6 +118,7 @@ struct TcParams {
   const float* x; FrameAddr fa; int64_t N;
   int stage0, n_q;
   int64_t* codes; float* residual_out; double* sqerr;
+  float* ema_counts; float* ema_sum;   // EMA statistics of core_vq.py:227-228 ([n_q, K] / [n_q, K, D], accumulated) or nullptr
   int ste;
   int bkt;                 // codes as [B, n_q, T] (RVQ_FLAG_CODES_BKT)
   int direct;              // exact re-scores use the k-means distance sum((x - c)^2) of core_vq.py:86-91 (RVQ_FLAG_DIRECT_DIST)
@@ -126,6 +127,10 @@ struct TcParams {
 };
 
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
+// vector reduction into global memory (no return value: the adds are settled by the L2)
+__device__ __forceinline__ void red_add_f4(float* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // residual element group: 16-byte chunk ch (dims 4ch..4ch+3) of frame f, XOR-swizzled with the frame number (its low
 // three bits reversed) so that all three access patterns of the kernel spread over the banks: 8 lanes = 8 consecutive
 // chunks of one frame; 8 lanes = 8 consecutive frames, one chunk; 8 lanes = 2 consecutive frames x 4 consecutive chunks
@@ -462,11 +467,17 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
       if (ob < best || (ob == best && oc < bcode)) { best = ob; bcode = oc; }
     }
     if (bcode == 0x7fffffff) bcode = it.cd.x;                   // NaN distances only: the first candidate
+    const int64_t nfr = tile_n0 + it.f;
     if (it.ck == bcode) {                                        // the winner's quarter holds its row: r <- r - q
       #pragma unroll
       for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(rs + rs_off(it.f, 8 * k + j)) = sub_row<TRAIN>(p, it.rl[k], it.w[k]);
+      if (TRAIN && p.ema_sum != nullptr && it.f < p.tf && nfr < p.N) {      // EMA statistics: embed_sum[code] += r, counts[code] += 1
+        float* row = p.ema_sum + (size_t(s) * p.K + bcode) * 128 + 4 * j;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) red_add_f4(row + 32 * k, it.rl[k]);
+        if (j == 0) atomicAdd(p.ema_counts + size_t(s) * p.K + bcode, 1.f);
+      }
     }
-    const int64_t nfr = tile_n0 + it.f;
     if (lane == 0) {
       *reinterpret_cast<int*>(ms + Sm::m_cand + it.f * 16) = bcode;
       if (it.f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = bcode;
@@ -488,9 +499,10 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     RVQ_TRACE3(trX, trn, u, 1);
   }
   float4 qa[8], qb[8];
+  int codeA = cand[fA].x, codeB = cand[fB].x;
   {
-    const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
-    const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
+    const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(codeA) * 128) + m;
+    const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(codeB) * 128) + m;
     #pragma unroll
     for (int i = 0; i < 8; ++i) qa[i] = nA == 1 ? __ldg(ra + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     #pragma unroll
@@ -510,12 +522,14 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
         return code;
       };
       if (nA == kBig) {
-        const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(wide_winner(fA)) * 128) + m;
+        codeA = wide_winner(fA);
+        const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(codeA) * 128) + m;
         #pragma unroll
         for (int i = 0; i < 8; ++i) qa[i] = __ldg(ra + 4 * i);
       }
       if (nB == kBig) {
-        const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(wide_winner(fB)) * 128) + m;
+        codeB = wide_winner(fB);
+        const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(codeB) * 128) + m;
         #pragma unroll
         for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
       }
@@ -527,21 +541,27 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   // to tensor memory, a_ready.  Phase 2 (off that chain): residual rows back to shared memory, exact rounding residue of
   // the operand, squared error; the caller publishes it on dr_ready, which the score warps await before their winner phase.
   uint32_t w[32];
-  auto sub_pack = [&](int f, float4 (&qr)[8], int half, bool done) {
+  auto sub_pack = [&](int f, float4 (&qr)[8], int half, bool done, int code) {
     const int sw = rs_swz(f);
     const float* rbase = rs + f * 128 + ((m ^ (sw & 3)) << 2);
+    // EMA statistics of the training forward (core_vq.py:227-228): the stage's input residual is added to its code's row
+    // of embed_sum (frames with a candidate list were counted by the warp that settled them)
+    const bool stats = TRAIN && p.ema_sum != nullptr && !done && f < p.tf && tile_n0 + f < p.N;
+    float* srow = stats ? p.ema_sum + (size_t(s) * p.K + code) * 128 + 4 * m : nullptr;
+    if (stats && m == 0) atomicAdd(p.ema_counts + size_t(s) * p.K + code, 1.f);
     #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 rv = *reinterpret_cast<const float4*>(rbase + ((i ^ (sw >> 2)) << 4));
+      if (TRAIN && stats) red_add_f4(srow + 16 * i, rv);
       const float4 n = done ? rv : sub_row<TRAIN>(p, rv, qr[i]);
       qr[i] = n;
       w[4 * i + 2 * half] = pack_half2(n.x, n.y);
       w[4 * i + 2 * half + 1] = pack_half2(n.z, n.w);
     }
   };
-  sub_pack(fA, qa, 0, doneA);
+  sub_pack(fA, qa, 0, doneA, codeA);
   RVQ_TRACE3(trX, trn, u, 4);
-  sub_pack(fB, qb, 1, doneB);
+  sub_pack(fB, qb, 1, doneB, codeB);
   RVQ_TRACE3(trX, trn, u, 5);
   if (store) {
     ptx::tmem_st_16x256b_x8(taddr, w);
@@ -1098,6 +1118,7 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   p.x = a.x; p.fa = FrameAddr{a.sxb, a.sxd, a.sxt, a.T}; p.N = N;
   p.stage0 = a.stage0; p.n_q = a.n_q;
   p.codes = a.codes; p.residual_out = a.residual_out; p.sqerr = a.sqerr;
+  p.ema_counts = a.ema_counts; p.ema_sum = a.ema_sum;
   p.ste = (a.flags & RVQ_FLAG_STE) ? 1 : 0;
   p.bkt = (a.flags & RVQ_FLAG_CODES_BKT) ? 1 : 0;
   p.direct = (a.flags & RVQ_FLAG_DIRECT_DIST) ? 1 : 0;
@@ -1112,7 +1133,7 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   const unsigned grid = unsigned(ntiles < sm_count ? ntiles : sm_count);
   // the lean variant serves plain encodes; straight-through arithmetic, loss numerators and the residual output
   // live in the other one (a stage's hot code has to fit the instruction cache)
-  if (p.ste || p.direct || p.sqerr != nullptr || p.residual_out != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, Sm::total, st>>>(p);
+  if (p.ste || p.direct || p.sqerr != nullptr || p.residual_out != nullptr || p.ema_sum != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, Sm::total, st>>>(p);
   else tc_encode_kernel<false><<<grid, kThreadsTc, Sm::total, st>>>(p);
   RVQ_LAUNCH_CHECK("tc_encode_kernel");
   if (a.quantized != nullptr)

@@ -257,12 +257,16 @@ class EuclideanCodebook(nn.Module):
 
 
 def _update_stack(codebooks: tp.Sequence[EuclideanCodebook], pk: ops.CodebookPack, x_bdt: torch.Tensor,
-                  codes: torch.Tensor, stage0: int, flags: int) -> None:
+                  codes: torch.Tensor, stage0: int, flags: int, stats: tp.Optional[torch.Tensor] = None) -> None:
     """EMA update of core_vq.py:227-235 for a run of stages at once: bincount + per-code residual
-    sums (``rvq_ema_stats``), with ``distrib.sync_buffers(True)`` ONE all-reduce of the packed statistics
+    sums (``stats``: already accumulated by the search, ``rvq_encode_train``; else ``rvq_ema_stats`` from the codes),
+    with ``distrib.sync_buffers(True)`` ONE all-reduce of the packed statistics
     across the frame shards (the role of distrib.all_reduce, distrib.py:32-34), then EMA / Laplace smoothing /
     table overwrite in place (``rvq_ema_apply``)."""
-    flat, counts, esum = ops.ema_stats(pk, x_bdt, codes, stage0, flags)
+    if stats is not None:
+        flat, counts, esum = ops.ema_stats_views(stats, len(codebooks), pk.K, pk.D)
+    else:
+        flat, counts, esum = ops.ema_stats(pk, x_bdt, codes, stage0, flags)
     if distrib.sync_enabled():                     # opt-in (distrib.sync_buffers): statistics of the global batch
         distrib.all_reduce_stats(flat)
     cb0 = codebooks[0]
@@ -431,13 +435,17 @@ def _stack_forward(layers: tp.Sequence[VectorQuantization], x: torch.Tensor, n_q
             # adds, core_vq.py:348-349), so the fused search hands back its final residual and the quantized sum is one
             # elementwise pass instead of a second walk over all stages' rows; fp32 rounding differs from the reference's
             # running sum by a few ulp (<< the 1e-5 bar).  Eval keeps the ordered sum of gathered rows (bit-exact).
-            codes, _, sqerr, res = ops.encode(pk, xd, 0, n_q, want_sqerr=cw > 0, want_residual=True, flags=flags)
+            # The EMA statistics (core_vq.py:227-228) come out of the same launch: the search adds each stage's input
+            # residual to its code's row while the row is on chip (rvq_encode_train).
+            stats = ops.ema_stats_buffer(n_q, pk.K, pk.D, xd.device)
+            codes, _, sqerr, res = ops.encode(pk, xd, 0, n_q, want_sqerr=cw > 0, want_residual=True, flags=flags,
+                                              ema_stats_out=stats)
             quant = (xd - res.permute(0, 2, 1)) if out_bdt else (xd.permute(0, 2, 1) - res)
             if out_bdt and not quant.is_contiguous():
                 quant = quant.contiguous()
             with torch.no_grad():
                 _expire_stack(layers, pk, xd, codes, 0, flags)
-                _update_stack(cbs, pk, xd, codes, 0, flags)
+                _update_stack(cbs, pk, xd, codes, 0, flags, stats=stats)
         else:
             codes, quant, sqerr, _ = ops.encode(pk, xd, 0, n_q, want_quantized=True, flags=flags, out_bdt=out_bdt)
     else:

@@ -81,6 +81,16 @@ int rvq_encode(const void* pack, int K, int D,
                int64_t* codes, float* quantized, float* residual_out, double* stage_sqerr,
                int flags, void* stream);
 
+/* ---- training forward in one launch: rvq_encode plus the EMA statistics of core_vq.py:227-228 -- what rvq_ema_stats
+ * computes from the codes afterwards, accumulated by the search itself while each stage's input residual is on chip
+ * (counts fp32 [n_q, K] = embed_onehot.sum(0), embed_sum fp32 [n_q, K, D] = (x^T @ onehot)^T; both zeroed by the call;
+ * float atomics: sums agree with rvq_ema_stats to summation order).  Other arguments as rvq_encode.           */
+int rvq_encode_train(const void* pack, int K, int D,
+                     const float* x, int64_t sxb, int64_t sxd, int64_t sxt, int B, int T,
+                     int stage0, int n_q,
+                     int64_t* codes, float* quantized, float* residual_out, double* stage_sqerr,
+                     float* counts, float* embed_sum, int flags, void* stream);
+
 /* ---- decode: replaces ResidualVectorQuantization.decode (core_vq.py:369-375).
  *   codes  int64 [n_q, B, T] with ELEMENT strides (scq, scb, sct) (model.py:188 passes a transposed view)
  *   out    fp32 [B, T, D] contiguous: ((0 + e_0[c_0]) + e_1[c_1]) + ...                          */

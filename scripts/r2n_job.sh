@@ -1,1 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k degenerate 2>&1 | grep -v "^$" | tail -30
+python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+python scripts/time_train_pieces.py 2>&1 | tail -4
+python scripts/time_train_repeat.py 2>&1 | grep -v "norm quant" | grep "grad"

@@ -168,6 +168,44 @@ def test_degenerate_tables_hundreds_of_candidates(mode):
     assert c["wide"] > 100 and c["wide_candidates"] > 30 * c["wide"], c
 
 
+def test_fused_ema_statistics_match_the_statistics_pass():
+    """rvq_encode_train: the EMA statistics the search accumulates itself (core_vq.py:227-228) against rvq_ema_stats run on
+    the same codes, and against a bincount / index_add of the oracle's residual chain (ragged frame count: padded tile
+    rows must not be counted; fitted-like tables so that candidate lists and wide sets contribute too)."""
+    from encodec_pytorch_b200 import _ops as ops, _lib as L
+    case = C.Case("fused_stats", 5, 128, 333, 1024, 6, 75, None, 4321, 21)
+    q = build_module(case).eval()
+    with torch.no_grad():
+        e = q.vq.layers[1]._codebook.embed
+        e[::3] *= 0.05                                        # heterogeneous norms: the per-code bound and its lists
+        e[100:140] = e[7] + 1e-6 * torch.randn(40, 128, device="cuda")      # a crowd: wide sets
+    q.vq.invalidate()
+    states = module_states(q)
+    x = C.latents(case.b, case.d, case.t, case.x_seed)
+    x[2, :, :40] = 2.0 * states[1]["embed"][7][:, None] + 0.2 * x[2, :, :40]
+    xc = x.cuda()
+    pk = q.vq._stack_pack()
+    n_q, K, D = 6, 1024, 128
+    for flags in (0, L.FLAG_STE):
+        stats = ops.ema_stats_buffer(n_q, K, D, xc.device)
+        codes, _, _, _ = ops.encode(pk, xc, 0, n_q, want_sqerr=True, want_residual=True, flags=flags, ema_stats_out=stats)
+        _, counts, esum = ops.ema_stats_views(stats, n_q, K, D)
+        _, counts2, esum2 = ops.ema_stats(pk, xc, codes, 0, flags)
+        assert torch.equal(counts, counts2)
+        torch.testing.assert_close(esum, esum2, rtol=1e-5, atol=1e-5 * float(esum2.abs().max()))
+        # oracle chain on the kernel's codes
+        res = O.frames_of(x)
+        for i in range(n_q):
+            idx = codes[i].reshape(-1).cpu()
+            assert torch.equal(counts[i].cpu(), torch.bincount(idx, minlength=K).float())
+            want = torch.zeros(K, D).index_add_(0, idx, res)
+            torch.testing.assert_close(esum[i].cpu(), want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+            qv = O.lookup(idx, states[i]["embed"])
+            if flags:
+                qv = res + (qv - res)
+            res = res - qv
+
+
 def test_layout_and_edge_cases():
     case = C.Case("edge", 3, 128, 17, 1024, 8, 75, None, 77, 2)
     q = build_module(case).eval()
