@@ -54,16 +54,13 @@ constexpr int kFull = 6;                // ncnt marker: exact scan of the whole 
 constexpr int kRsBytes = kM * 128 * 4;  // fp32 residual of one tile
 
 struct Sm {
-  // augmented K block of the A operand (K-step 8), no swizzle: k-group 0 of slot 0, k-group 0 of slot 1 (per frame:
-  // 1, 1, R0, 0, R1, 0, 0, 0 -- the ones meet the hi/lo halves of |c|^2, R0 + R1 >= |r| meets -g16_k when the stage uses
-  // the per-code bound), then the all-zero k-group 1 shared by both slots
-  static constexpr uint32_t aug = 0;
-  static constexpr uint32_t ring = aug + 6144;
+  static constexpr uint32_t aug = 0;                               // [2 k-groups][128 rows][16 B], no swizzle
+  static constexpr uint32_t ring = aug + 4096;
   static constexpr uint32_t rs = ring + kRing * kSlotBytes;        // 2 x fp32 [128 f][128 d], chunk-swizzled
   static constexpr uint32_t misc = rs + 2 * kRsBytes;              // 2 x per-slot block (offsets m_*)
   static constexpr uint32_t m_cand = 0;                            // int4 [128]: candidate codes (-1 = none)
-  static constexpr uint32_t m_ncnt = m_cand + kM * 16;             // u8 [128]
-  static constexpr uint32_t m_cmask = m_ncnt + kM;                 // u32 [128] flagged classes   (a fresh tile: |x|^2 of dims 0..63)
+  static constexpr uint32_t m_ncnt = m_cand + kM * 16;             // int [128]
+  static constexpr uint32_t m_cmask = m_ncnt + kM * 4;             // u32 [128] flagged classes   (a fresh tile: |x|^2 of dims 0..63)
   static constexpr uint32_t m_bmask = m_cmask + kM * 4;            // u32 [128] flagged batches   (a fresh tile: |x|^2 of dims 64..127)
   static constexpr uint32_t m_dr2 = m_bmask + kM * 4;              // float [2][128]: |r - fp16(r)|^2 of the current operand, per half of the dims
   static constexpr uint32_t m_slowq = m_dr2 + 2 * kM * 4;          // u8 [128]: frames with 2..4 listed candidates
@@ -71,13 +68,13 @@ struct Sm {
   static constexpr uint32_t m_qcnt = m_wideq + kM;                 // int [2]: queue lengths {slow, wide}
   static constexpr uint32_t m_size = m_qcnt + 16;
   static constexpr uint32_t bars = misc + 2 * m_size;
-  static constexpr uint32_t total = bars + 224;
+  static constexpr uint32_t total = bars + 256;
 };
 struct Bars {
   uint64_t full[kRing], empty[kRing], acc_full[kAccBufs], acc_empty[kAccBufs], a_ready[2], cand_ready[2], dr_ready[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 224, "barrier block");
+static_assert(sizeof(Bars) <= 256, "barrier block");
 // shared-window address of a barrier, from the CTA's window base (no generic->shared conversion inside the hot loops)
 #define RVQ_BAR(field, i) (sbase + Sm::bars + uint32_t(offsetof(Bars, field)) + 8u * uint32_t(i))
 static_assert(Sm::total <= 227 * 1024, "shared memory budget");
@@ -118,7 +115,6 @@ struct TcParams {
   const float* x; FrameAddr fa; int64_t N;
   int stage0, n_q;
   int64_t* codes; float* residual_out; double* sqerr;
-  float* ema_counts; float* ema_sum;   // EMA statistics of core_vq.py:227-228 ([n_q, K] / [n_q, K, D], accumulated) or nullptr
   int ste;
   int bkt;                 // codes as [B, n_q, T] (RVQ_FLAG_CODES_BKT)
   int direct;              // exact re-scores use the k-means distance sum((x - c)^2) of core_vq.py:86-91 (RVQ_FLAG_DIRECT_DIST)
@@ -127,10 +123,6 @@ struct TcParams {
 };
 
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
-// vector reduction into global memory (no return value: the adds are settled by the L2)
-__device__ __forceinline__ void red_add_f4(float* addr, const float4& v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 // residual element group: 16-byte chunk ch (dims 4ch..4ch+3) of frame f, XOR-swizzled with the frame number (its low
 // three bits reversed) so that all three access patterns of the kernel spread over the banks: 8 lanes = 8 consecutive
 // chunks of one frame; 8 lanes = 8 consecutive frames, one chunk; 8 lanes = 2 consecutive frames x 4 consecutive chunks
@@ -182,8 +174,7 @@ __device__ __forceinline__ float residue_of(float a, float b, uint32_t word, flo
   return fmaf(eb, eb, fmaf(ea, ea, e2));
 }
 
-// tiles [start, start+cnt) of this CTA (contiguous ranges: measured 1 % faster at cfg2 than the interleaved order
-// blockIdx.x + j * gridDim.x, whose only merit is to spread a stretch of expensive frames over more CTAs)
+// tiles [start, start+cnt) of this CTA
 __device__ __forceinline__ void cta_range(int ntiles, int& start, int& cnt) {
   const int base = ntiles / int(gridDim.x), rem = ntiles % int(gridDim.x);
   const int b = blockIdx.x;
@@ -249,7 +240,7 @@ __device__ __forceinline__ void resolve_full(const float* rs, unsigned char* ms,
   if (lane == 0) {
     const int code = bcode == 0x7fffffff ? 0 : bcode;
     *reinterpret_cast<int4*>(ms + Sm::m_cand + f * 16) = make_int4(code, -1, -1, -1);
-    ms[Sm::m_ncnt + f] = 1;
+    *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = 1;
     if (code_out != nullptr) *code_out = code;
   }
   __syncwarp();
@@ -303,9 +294,9 @@ template <int NC> struct Cand { int c[NC]; Row4 w[NC]; float nrm[NC]; };
 template <int NC>
 __device__ __forceinline__ void load_cand(Cand<NC>& k, int j, const float* __restrict__ t32, const float* __restrict__ cn) {
   #pragma unroll
-  for (int u = 0; u < NC; ++u) {      // (unconditional: a conditionally initialised struct is kept in local memory)
-    const int c = k.c[u] < 0 ? 0 : k.c[u];
-    k.w[u] = load_row(t32, c, j); k.nrm[u] = __ldg(cn + c);
+  for (int u = 0; u < NC; ++u) {
+    k.nrm[u] = 0.f;
+    if (k.c[u] >= 0) { k.w[u] = load_row(t32, k.c[u], j); k.nrm[u] = __ldg(cn + k.c[u]); }
   }
 }
 // exact distances of up to NC candidates (core_vq.py:183-187); keeps the best (lowest code on ties) and its slot u
@@ -327,58 +318,56 @@ __device__ __forceinline__ void score_cand(const Cand<NC>& k, const Row4& r, flo
     if (k.c[u] >= 0 && (e < best || (e == best && k.c[u] < bcode))) { best = e; bcode = k.c[u]; bidx = u; }
   }
 }
-// A frame whose flagged batches x flagged classes give more than 4 candidates: ALL update warps work on it, two candidates per
-// quarter-warp and step (64 per step), exact fp32 distances (core_vq.py:183-187).  Every quarter folds its best into the
-// frame's 64-bit key {orderable distance, code} with a shared-memory atomicMin -- smallest distance, lowest code on ties; the
-// key lives in the upper half of the frame's candidate entry, which the score warp left at all ones -- and the winner is read
-// after the update warps' barrier.  (Degenerate tables -- hundreds of near-identical codes -- give candidate sets of several
-// hundred codes: one warp per frame, 8 candidates per step, took 100 k cycles for such a frame.)
 template <bool TRAIN>
-__device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs, unsigned char* ms, int f, int u, int lane, int rot, int nchunks,
-                                             const float* __restrict__ t32, const float* __restrict__ cn) {
+__device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs, unsigned char* ms, int f, int lane, int s, int rot, int nchunks,
+                                             int64_t tile_n0, const float* __restrict__ t32, const float* __restrict__ cn) {
   const int qq = lane >> 3, j = lane & 7;
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
   const uint32_t bm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + f * 4);
-  const int nc = __popc(cm), total = nc * __popc(bm);
-#ifndef RVQ_WIDE_KPER
-#define RVQ_WIDE_KPER 4
-#endif
-  constexpr int kPer = RVQ_WIDE_KPER;                      // candidates per quarter-warp and step
-#ifdef RVQ_WIDE_OWNER      // A/B builds: the frame's first warp alone
-  if (u != 0) return;
-  constexpr int kCoop = 1;
-#else
-  constexpr int kCoop = kUpdWarps;
-#endif
-  if (4 * kPer * u >= total) return;                       // (warp-uniform) no candidate left for this warp
-  const int w = 4 * u + qq;                                // this quarter's number among the 32 of the update warps
-  // lane L: position of the L-th flagged batch / class (candidate t = flagged batch t / nc, flagged class t % nc)
-  uint32_t mb = bm, mc = cm;
-  const int npos = min(lane, max(nc, total / nc));         // (positions beyond the populations are never asked for)
-  for (int i = 0; i < npos; ++i) { mb &= mb - 1; mc &= mc - 1; }
-  const int posb = mb ? __ffs(mb) - 1 : 0, posc = mc ? __ffs(mc) - 1 : 0;
-  const float inv_nc = 1.f / float(nc);
+  const int nc = __popc(cm);
   const Row4 r = load_res(rs, f, j);
   const float rr = quarter_sum(dot_row(r, r));
   float best = inf_f(); int bcode = 0x7fffffff, bidx = 0;
+  // quarter qq takes the flagged batches number qq, qq + 4, ...; within a batch the flagged classes two at a time
+  uint32_t bmq = bm;
+  for (int i = 0; i < qq; ++i) bmq &= bmq - 1;
+  const int nb = __popc(bm);
   #pragma unroll 1
-  for (int t0 = 0; t0 < total; t0 += 4 * kPer * kCoop) {
-    Cand<kPer> k;
+  for (int ob = 0; ob < nb; ob += 4) {
+    const int a = bmq ? __ffs(bmq) - 1 : -1;
     #pragma unroll
-    for (int v = 0; v < kPer; ++v) {
-      const int t = t0 + kPer * w + v;
-      const int ia = int((float(t) + 0.5f) * inv_nc);      // exact for t < 1024, nc <= 32
-      const int ic = t - ia * nc;
-      const int a = __shfl_sync(0xffffffffu, posb, ia & 31), jj = __shfl_sync(0xffffffffu, posc, ic & 31);
-      k.c[v] = t < total ? code_of(a, jj, rot, nchunks) : -1;
+    for (int i = 0; i < 4; ++i) bmq &= bmq - 1;
+    uint32_t cmq = cm;
+    #pragma unroll 1
+    for (int oc = 0; oc < nc; oc += 2) {
+      Cand<2> k;
+      #pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int jj = cmq ? __ffs(cmq) - 1 : -1;
+        cmq &= cmq - 1;
+        k.c[u] = (a >= 0 && jj >= 0) ? code_of(a, jj, rot, nchunks) : -1;
+      }
+      load_cand<2>(k, j, t32, cn);
+      score_cand<2>(k, r, rr, best, bcode, bidx, TRAIN && p.direct);
     }
-    load_cand<kPer>(k, j, t32, cn);
-    score_cand<kPer>(k, r, rr, best, bcode, bidx, TRAIN && p.direct);
   }
-  if (j == 0 && bcode != 0x7fffffff) {                     // (NaN distances never enter: the key then stays at all ones)
-    uint32_t b = __float_as_uint(best + 0.f);              // -0 -> +0; then the usual order-preserving map to unsigned
-    b ^= (b >> 31) ? 0xffffffffu : 0x80000000u;
-    atomicMin(reinterpret_cast<unsigned long long*>(ms + Sm::m_cand + f * 16 + 8), (static_cast<unsigned long long>(b) << 32) | uint32_t(bcode));
+  // best over the four quarters (candidate codes are distinct, so the winner's quarter is unique)
+  float wb = best; int wc = bcode;
+  #pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, wb, off);
+    const int oc = __shfl_xor_sync(0xffffffffu, wc, off);
+    if (ob < wb || (ob == wb && oc < wc)) { wb = ob; wc = oc; }
+  }
+  bool mine = bcode == wc;
+  if (wc == 0x7fffffff) {                                  // NaN distances only: lowest candidate, like an exact scan would
+    mine = qq == 0;
+    if (mine) bcode = code_of(__ffs(bm) - 1, __ffs(cm) - 1, rot, nchunks);
+  }
+  const int64_t nfr = tile_n0 + f;
+  if (mine && j == 0) {
+    *reinterpret_cast<int*>(ms + Sm::m_cand + f * 16) = bcode;      // the frame now has a single (exact) winner
+    if (f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = bcode;
   }
 }
 
@@ -403,7 +392,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   const int* qc = reinterpret_cast<const int*>(ms + Sm::m_qcnt);
   const int nslow = qc[0], nwide = qc[1];
   const int4* cand = reinterpret_cast<const int4*>(ms + Sm::m_cand);
-  const unsigned char* ncnt = ms + Sm::m_ncnt;
+  const int* ncnt = reinterpret_cast<const int*>(ms + Sm::m_ncnt);
   const int g = lane >> 2, m = lane & 3;
   const int fA = q * 32 + h * 16 + g, fB = fA + 8;
   // The winner rows of the certified frames are requested FIRST: they are in flight while the listed frames are resolved.
@@ -477,17 +466,11 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
       if (ob < best || (ob == best && oc < bcode)) { best = ob; bcode = oc; }
     }
     if (bcode == 0x7fffffff) bcode = it.cd.x;                   // NaN distances only: the first candidate
-    const int64_t nfr = tile_n0 + it.f;
     if (it.ck == bcode) {                                        // the winner's quarter holds its row: r <- r - q
       #pragma unroll
       for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(rs + rs_off(it.f, 8 * k + j)) = sub_row<TRAIN>(p, it.rl[k], it.w[k]);
-      if (TRAIN && p.ema_sum != nullptr && it.f < p.tf && nfr < p.N) {      // EMA statistics: embed_sum[code] += r, counts[code] += 1
-        float* row = p.ema_sum + (size_t(s) * p.K + bcode) * 128 + 4 * j;
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) red_add_f4(row + 32 * k, it.rl[k]);
-        if (j == 0) atomicAdd(p.ema_counts + size_t(s) * p.K + bcode, 1.f);
-      }
     }
+    const int64_t nfr = tile_n0 + it.f;
     if (lane == 0) {
       *reinterpret_cast<int*>(ms + Sm::m_cand + it.f * 16) = bcode;
       if (it.f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = bcode;
@@ -503,17 +486,15 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
       item_load(i, it0);
       item_finish(it0);
     }
-    // wide candidate sets: one frame at a time, all warps together
+    // wide candidate sets: one frame per warp at a time, handed out from the last warp down
     #pragma unroll 1
-    // (the first candidates of frame i go to warp 7 - i, 6 - i, ...: the warps at the low end hold most of the listed frames)
-    for (int i = 0; i < nwide; ++i) resolve_wide<TRAIN>(p, rs, ms, wideq[i], (kUpdWarps - 1 - u + i) & (kUpdWarps - 1), lane, rot, nchunks, t32, cn);
+    for (int i = kUpdWarps - 1 - u; i < nwide; i += kUpdWarps) resolve_wide<TRAIN>(p, rs, ms, wideq[i], lane, s, rot, nchunks, tile_n0, t32, cn);
     RVQ_TRACE3(trX, trn, u, 1);
   }
   float4 qa[8], qb[8];
-  int codeA = cand[fA].x, codeB = cand[fB].x;
   {
-    const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(codeA) * 128) + m;
-    const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(codeB) * 128) + m;
+    const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
+    const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
     #pragma unroll
     for (int i = 0; i < 8; ++i) qa[i] = nA == 1 ? __ldg(ra + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     #pragma unroll
@@ -523,24 +504,13 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     ptx::named_bar_sync(6, kUpdWarps * 32);      // listed frames are updated, wide frames have their winner
     RVQ_TRACE3(trX, trn, u, 2);
     if (nwide > 0 && __any_sync(0xffffffffu, nA == kBig || nB == kBig)) {
-      // winners of the wide sets: low word of the frame's key (all ones = NaN distances only: the first candidate, like an
-      // exact scan would answer); the group's first lane writes the code out
-      auto wide_winner = [&](int f) {
-        const int4 cd = cand[f];
-        const int code = cd.z == -1 ? cd.x : cd.z;
-        const int64_t nfr = tile_n0 + f;
-        if (m == 0 && f < p.tf && nfr < p.N) p.codes[code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr)] = code;
-        return code;
-      };
+      const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(cand[fA].x) * 128) + m;
+      const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(cand[fB].x) * 128) + m;
       if (nA == kBig) {
-        codeA = wide_winner(fA);
-        const float4* ra = reinterpret_cast<const float4*>(t32 + size_t(codeA) * 128) + m;
         #pragma unroll
         for (int i = 0; i < 8; ++i) qa[i] = __ldg(ra + 4 * i);
       }
       if (nB == kBig) {
-        codeB = wide_winner(fB);
-        const float4* rb = reinterpret_cast<const float4*>(t32 + size_t(codeB) * 128) + m;
         #pragma unroll
         for (int i = 0; i < 8; ++i) qb[i] = __ldg(rb + 4 * i);
       }
@@ -552,27 +522,21 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
   // to tensor memory, a_ready.  Phase 2 (off that chain): residual rows back to shared memory, exact rounding residue of
   // the operand, squared error; the caller publishes it on dr_ready, which the score warps await before their winner phase.
   uint32_t w[32];
-  auto sub_pack = [&](int f, float4 (&qr)[8], int half, bool done, int code) {
+  auto sub_pack = [&](int f, float4 (&qr)[8], int half, bool done) {
     const int sw = rs_swz(f);
     const float* rbase = rs + f * 128 + ((m ^ (sw & 3)) << 2);
-    // EMA statistics of the training forward (core_vq.py:227-228): the stage's input residual is added to its code's row
-    // of embed_sum (frames with a candidate list were counted by the warp that settled them)
-    const bool stats = TRAIN && p.ema_sum != nullptr && !done && f < p.tf && tile_n0 + f < p.N;
-    float* srow = stats ? p.ema_sum + (size_t(s) * p.K + code) * 128 + 4 * m : nullptr;
-    if (stats && m == 0) atomicAdd(p.ema_counts + size_t(s) * p.K + code, 1.f);
     #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 rv = *reinterpret_cast<const float4*>(rbase + ((i ^ (sw >> 2)) << 4));
-      if (TRAIN && stats) red_add_f4(srow + 16 * i, rv);
       const float4 n = done ? rv : sub_row<TRAIN>(p, rv, qr[i]);
       qr[i] = n;
       w[4 * i + 2 * half] = pack_half2(n.x, n.y);
       w[4 * i + 2 * half + 1] = pack_half2(n.z, n.w);
     }
   };
-  sub_pack(fA, qa, 0, doneA, codeA);
+  sub_pack(fA, qa, 0, doneA);
   RVQ_TRACE3(trX, trn, u, 4);
-  sub_pack(fB, qb, 1, doneB, codeB);
+  sub_pack(fB, qb, 1, doneB);
   RVQ_TRACE3(trX, trn, u, 5);
   if (store) {
     ptx::tmem_st_16x256b_x8(taddr, w);
@@ -614,11 +578,8 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
 
 }  // namespace
 
-// PC: some stage of the call certifies with the per-code bound (StageMeta::percode; bit s of pcmask = stage stage0 + s).  The
-// kernel picks the specialisation at its top, so a stack on the per-stage bound runs code that does not contain the per-code
-// branch at all (its mere presence in the winner phase cost 1.8 % at cfg2).
-template <bool TRAIN, bool PC>
-__device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned long long pcmask) {
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
   Bars* bars = reinterpret_cast<Bars*>(smem + Sm::bars);
@@ -646,10 +607,9 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
     int* qc = reinterpret_cast<int*>(smem + Sm::misc + threadIdx.x * Sm::m_size + Sm::m_qcnt);
     qc[0] = 0; qc[1] = 0;
   }
-  // augmented K block of A: k-group 0 of each slot = (1, 1, 0, ...) picks up hi/lo of |c|^2 (the per-frame bounds of |r|
-  // are written per stage), k-group 1 = 0
-  for (int i = threadIdx.x; i < 6144 / 16; i += blockDim.x)
-    *reinterpret_cast<uint4*>(smem + Sm::aug + i * 16) = make_uint4(i < 256 ? pack_half2(1.f, 1.f) : 0u, 0u, 0u, 0u);
+  // constant augmented K block of A: k-group 0 = (1, 1, 0, ...) picks up hi/lo of |c|^2, k-group 1 = 0
+  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
+    *reinterpret_cast<uint4*>(smem + Sm::aug + i * 16) = make_uint4(i < 128 ? pack_half2(1.f, 1.f) : 0u, 0u, 0u, 0u);
   if (warp == 13) {
     ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
     ptx::tmem_relinquish();
@@ -660,10 +620,10 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 #ifdef RVQ_TC_TRACE
-  long long* s_t0 = reinterpret_cast<long long*>(smem + Sm::bars + 216);      // padding of the barrier block
-  if (threadIdx.x == 0) *s_t0 = clock64();
+  __shared__ long long s_t0;
+  if (threadIdx.x == 0) s_t0 = clock64();
   __syncthreads();
-  const long long t_kernel0 = *s_t0;
+  const long long t_kernel0 = s_t0;
 #endif
 
   if (warp >= 12) {
@@ -703,9 +663,7 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
       // lane issues), so the operands of tcgen05.mma stay in uniform registers and a chunk costs a few dozen instructions. =====
       constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kM, kN);
       const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem);      // a provably warp-uniform copy (uniform register)
-      // slot 0: k-group 0 at +0, slot 1: at +2048; the shared zero k-group 1 at +4096 (LBO 4096 / 2048)
-      const uint64_t ad_aug0 = ptx::umma_desc_kmajor_noswz(sb + Sm::aug, 4096, 128);
-      const uint64_t ad_aug1 = ptx::umma_desc_kmajor_noswz(sb + Sm::aug + 2048, 2048, 128);
+      const uint64_t ad_aug = ptx::umma_desc_kmajor_noswz(sb + Sm::aug, 2048, 128);
       const uint64_t bd0 = ptx::umma_desc_kmajor_noswz(sb + Sm::ring, kTcLBO, kTcSBO);
       const uint32_t bar_full0 = sb + Sm::bars + uint32_t(offsetof(Bars, full));
       const uint32_t bar_empty0 = sb + Sm::bars + uint32_t(offsetof(Bars, empty));
@@ -721,7 +679,6 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
           ptx::tc_fence_after();
           RVQ_TRACE(X, n, 0, lane == 0);
           const uint32_t a_tmem = tmem_u + kTmemA + 64 * X;
-          const uint64_t ad_aug = X ? ad_aug1 : ad_aug0;
           #pragma unroll 1
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t d_tmem = tmem_u + ab * kN;
@@ -765,7 +722,6 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + p.fa.base(n - lane) + int64_t(h * 64 + 32 + lane) * p.fa.sxd));
       }
     };
-    const int pc_first = PC ? int(pcmask & 1ull) : 0;
     auto load_tile = [&](int X, int tile) {
       float* rs = reinterpret_cast<float*>(smem + Sm::rs + X * kRsBytes);
       unsigned char* ms = smem + Sm::misc + X * Sm::m_size;
@@ -797,11 +753,6 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
       // |x|^2 of this half of the dims goes where the (not yet written) class / batch masks of the tile's first stage live
       reinterpret_cast<float*>(ms + (h ? Sm::m_bmask : Sm::m_cmask))[f] = xsum;
       reinterpret_cast<float*>(ms + Sm::m_dr2)[h * kM + f] = e2;
-      // per-code bound: this half's |x| (rounded up to fp16) goes to column 2 + 2h of the frame's augmented operand row;
-      // the two halves meet -g16_k in columns 2 and 4 of the image, and sqrt(a) + sqrt(b) >= sqrt(a + b) = |x|
-      *reinterpret_cast<uint32_t*>(smem + Sm::aug + X * 2048 + f * 16 + 4 + 4 * h) =
-          pc_first ? uint32_t(__half_as_ushort(__float2half_ru(sqrtf(xsum) * 1.0001f))) : 0u;
-      ptx::fence_proxy_async_smem();
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -883,7 +834,7 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
     const int q = warp;                        // TMEM lane quadrant = frames 32q..32q+31 of a tile
     const int f = q * 32 + lane;
     const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);
-    uint32_t n_cert = 0, n_resc = 0, n_full = 0, n_wide = 0, n_widec = 0;   // search statistics (rvq_search_counters)
+    uint32_t n_cert = 0, n_resc = 0, n_full = 0;                        // search statistics (rvq_search_stats)
 #ifdef RVQ_TC_TIMERS
     uint32_t t_wait = 0, t_epi = 0, t_win = 0;
     const long long t_begin = clock64();
@@ -907,9 +858,6 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
         // margin coefficients of this stage: requested before the chunk loop, used after it
         const float mt_coef = __ldg(&meta->margin_coef), mt_abs = __ldg(&meta->margin_abs), mt_xlimit = __ldg(&meta->xlimit);
         const float mt_cmax = __ldg(&meta->cmax_all), mt_dr = __ldg(&meta->margin_dr);
-        // per-code bound (StageMeta): this stage's switch and the next stage's (its operand's bound of |r| is written at the
-        // end of this one), from the mask gathered at kernel start
-        const int pc = PC && s < 64 ? int(pcmask >> s) & 1 : 0, pc_next = PC && s < 63 ? int(pcmask >> (s + 1)) & 1 : 0;
         RVQ_TICK0();
         // ---- scores: per-class and per-batch minima of the K approximate scores of this frame ----
         float cm[32], bmin[32];
@@ -984,29 +932,7 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
           m4[j] = fminf(m4[j], cm[8 * j + 7]);
         }
         const float m = fminf(ptx::fmin3(m4[0], m4[1], m4[2]), m4[3]);
-        float thr = m + delta;
-        if (pc) {
-          // Per-code bound: the accumulator holds the lower bounds T_k = S_k - g16_k R of the true scores.  For the code k'
-          // that attains the minimum of T (it must be the only one, else the per-stage bound serves):
-          //   s_winner <= s_k' <= T_k' + (g16_k' + a_k') R + b_k' |r - fp16(r)| + abs =: thr,
-          // and every code whose T exceeds thr is beaten by k'.
-          uint32_t ce4[4] = {0u, 0u, 0u, 0u}, be4[4] = {0u, 0u, 0u, 0u};
-          #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            // (volatile: the compiler must not hoist these out of the branch -- stages on the per-stage bound skip them)
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(ce4[j & 3]) : "f"(cm[j]), "f"(m), "r"(1u << j));
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(be4[j & 3]) : "f"(bmin[j]), "f"(m), "r"(1u << j));
-          }
-          const uint32_t ceq = (ce4[0] | ce4[1]) | (ce4[2] | ce4[3]);
-          const uint32_t beq = ((be4[0] | be4[1]) | (be4[2] | be4[3])) >> (32 - 4 * nchunks);
-          const bool uniq = __popc(ceq) == 1 && __popc(beq) == 1;
-          const float mt_abs_pc = __ldg(&meta->abs_pc), mt_g16max = __ldg(&meta->g16max);
-          const float2 ab = __ldg(pv.gab(st) + (uniq ? code_of(__ffs(beq) - 1, __ffs(ceq) - 1, rot, nchunks) : 0));
-          const uint4 arow = *reinterpret_cast<const uint4*>(smem + Sm::aug + X * 2048 + f * 16);
-          const float Rm = __half2float(__ushort_as_half((unsigned short)(arow.y & 0xffffu))) +
-                           __half2float(__ushort_as_half((unsigned short)(arow.z & 0xffffu)));      // the R the tensor core multiplied with
-          thr = uniq ? fmaf(ab.x, Rm, fmaf(ab.y, drn, m + mt_abs_pc)) : m + fmaf(mt_g16max, Rm, delta);
-        }
+        const float thr = m + delta;
         uint32_t cm4[4] = {0u, 0u, 0u, 0u}, bm4[4] = {0u, 0u, 0u, 0u};
         #pragma unroll
         for (int j = 0; j < 32; ++j) {                // two instructions per value: compare, predicated OR with an immediate
@@ -1034,7 +960,7 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
           cd.w = two ? code_of(b1, c1, rot, nchunks) : -1;
         }
         *reinterpret_cast<int4*>(ms + Sm::m_cand + f * 16) = cd;
-        ms[Sm::m_ncnt + f] = (unsigned char)(full ? kFull : (ncand > 4 ? kBig : ncand));
+        *reinterpret_cast<int*>(ms + Sm::m_ncnt + f * 4) = full ? kFull : (ncand > 4 ? kBig : ncand);
         *reinterpret_cast<uint32_t*>(ms + Sm::m_cmask + f * 4) = cmask;
         *reinterpret_cast<uint32_t*>(ms + Sm::m_bmask + f * 4) = bmask;
         int64_t* code_out = (f < p.tf && nfr < p.N) ? p.codes + code_index(p.bkt, p.n_q, p.fa.T, p.N, s, nfr) : nullptr;
@@ -1054,23 +980,11 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
           }
         }
         n_full += full ? 1u : 0u; n_cert += (!full && ncand == 1) ? 1u : 0u; n_resc += (!full && ncand > 1) ? 1u : 0u;
-#ifndef RVQ_NO_WIDE_COUNTERS
-        if (!full && ncand > 4) { n_wide += 1u; n_widec += uint32_t(ncand); }
-#endif
         // upper bound of the next residual's |r|^2 (only the margin and the validity test use it):
         // the winner's approximate score is <= m + delta and off by <= delta/2
         if (full) { const float g2 = xnorm + mt_cmax; xx = g2 * g2; }
-        else if (pc) xx = fmaxf(xx + thr, 0.f) * 1.00001f + 1e-30f;      // thr bounds the winner's true score
         else xx = fmaxf(xx + m + 1.5f * delta, 0.f) * 1.00001f + 1e-30f;
         if (X) xx_1 = xx; else xx_0 = xx;
-        if (s + 1 < p.n_q && (pc | pc_next)) {
-          // the next stage's augmented operand row: (1, 1, R, 0, 0, 0, 0, 0), R >= |r| rounded up to fp16 (0 switches the
-          // per-code term off; a row that is 0 and stays 0 is left alone: stacks with uniform norms never pay for the
-          // store and its proxy fence).  All MMAs of this stage have completed (their scores were consumed above).
-          const uint32_t rw = pc_next ? uint32_t(__half_as_ushort(__float2half_ru(sqrtf(xx) * 1.0001f))) : 0u;
-          *reinterpret_cast<uint4*>(smem + Sm::aug + X * 2048 + f * 16) = make_uint4(pack_half2(1.f, 1.f), rw, 0u, 0u);
-          ptx::fence_proxy_async_smem();
-        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(RVQ_BAR(cand_ready, X));    // winners and queues visible to the update warps
         RVQ_TRACE(X, n, 5, warp == 0 && lane == 0);
@@ -1084,13 +998,10 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
         n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
         n_resc += __shfl_xor_sync(0xffffffffu, n_resc, off);
         n_full += __shfl_xor_sync(0xffffffffu, n_full, off);
-        n_wide += __shfl_xor_sync(0xffffffffu, n_wide, off);
-        n_widec += __shfl_xor_sync(0xffffffffu, n_widec, off);
       }
       if (lane == 0) {
         atomicAdd(&p.counters[0], (unsigned long long)(n_cert + n_resc + n_full)); atomicAdd(&p.counters[1], (unsigned long long)n_cert);
         atomicAdd(&p.counters[2], (unsigned long long)n_resc); atomicAdd(&p.counters[3], (unsigned long long)n_full);
-        atomicAdd(&p.counters[11], (unsigned long long)n_wide); atomicAdd(&p.counters[12], (unsigned long long)n_widec);
 #ifdef RVQ_TC_TIMERS
         atomicAdd(&p.counters[4], (unsigned long long)t_wait); atomicAdd(&p.counters[5], (unsigned long long)t_epi);
         atomicAdd(&p.counters[6], (unsigned long long)t_win);
@@ -1104,22 +1015,6 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 13) ptx::tmem_dealloc(tmem, 512);
-}
-
-template <bool TRAIN>
-__global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams p) {
-  // which stages of this call use the per-code bound: gathered by every warp for itself (two L2 reads per lane at most).
-  // Stages beyond 63 use the per-stage bound, which is valid for every stage (their operand rows then carry R = 0).
-  const int lane = threadIdx.x & 31;
-  PackView pv(p.pack, p.K, 128);
-  const unsigned lo = __ballot_sync(0xffffffffu, lane < p.n_q && __ldg(&pv.meta(p.stage0 + lane)->percode) != 0);
-  const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < p.n_q && __ldg(&pv.meta(p.stage0 + (lane + 32 < p.n_q ? lane + 32 : 0))->percode) != 0);
-  unsigned long long pcmask = (static_cast<unsigned long long>(hi) << 32) | lo;
-#ifdef RVQ_NO_PERCODE      // A/B builds: the per-code branch switched off
-  pcmask = 0ull;
-#endif
-  if (pcmask != 0ull) tc_encode_body<TRAIN, true>(p, pcmask);
-  else tc_encode_body<TRAIN, false>(p, 0ull);
 }
 
 int tc_debug_trace(long long* out_host, int n) {
@@ -1150,7 +1045,6 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   p.x = a.x; p.fa = FrameAddr{a.sxb, a.sxd, a.sxt, a.T}; p.N = N;
   p.stage0 = a.stage0; p.n_q = a.n_q;
   p.codes = a.codes; p.residual_out = a.residual_out; p.sqerr = a.sqerr;
-  p.ema_counts = a.ema_counts; p.ema_sum = a.ema_sum;
   p.ste = (a.flags & RVQ_FLAG_STE) ? 1 : 0;
   p.bkt = (a.flags & RVQ_FLAG_CODES_BKT) ? 1 : 0;
   p.direct = (a.flags & RVQ_FLAG_DIRECT_DIST) ? 1 : 0;
@@ -1165,7 +1059,7 @@ int tc_encode(const EncodeArgs& a, cudaStream_t st) {
   const unsigned grid = unsigned(ntiles < sm_count ? ntiles : sm_count);
   // the lean variant serves plain encodes; straight-through arithmetic, loss numerators and the residual output
   // live in the other one (a stage's hot code has to fit the instruction cache)
-  if (p.ste || p.direct || p.sqerr != nullptr || p.residual_out != nullptr || p.ema_sum != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, Sm::total, st>>>(p);
+  if (p.ste || p.direct || p.sqerr != nullptr || p.residual_out != nullptr) tc_encode_kernel<true><<<grid, kThreadsTc, Sm::total, st>>>(p);
   else tc_encode_kernel<false><<<grid, kThreadsTc, Sm::total, st>>>(p);
   RVQ_LAUNCH_CHECK("tc_encode_kernel");
   if (a.quantized != nullptr)

@@ -1,3 +1,1 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -5
-python scripts/time_train_pieces.py 2>&1 | tail -4
-python scripts/time_train_repeat.py 2>&1 | grep -v "norm quant" | grep "grad"
+VARIANTS="prev:-@rvq_tc_prev.cu cur:- nocnt:RVQ_NO_WIDE_COUNTERS owner:RVQ_WIDE_OWNER both:RVQ_NO_WIDE_COUNTERS,RVQ_WIDE_OWNER" bash scripts/run_variants.sh
