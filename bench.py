@@ -32,7 +32,7 @@ FLOP_PER_FRAME_STAGE = 2 * BINS * D          # only the x.c^T co
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_encode_kernel launch at cfg2, from the committed ncu --set full
 # capture named below (NOT measured by this run: ncu replays kernels, a bench run must not sit under it).  Algorithmic:
 # 24.6 MB latents + 12.3 MB codes; the capture also sees the first touch of the 43 MB pack, which then stays in L2.
-NCU_TRAFFIC_FILE = "profiles/r2i_tc_encode_ncu_raw.csv"
+NCU_TRAFFIC_FILE = "profiles/r2p_tc_encode_ncu_raw.csv"
 
 
 def _ncu_traffic():
@@ -273,9 +273,12 @@ def _extras(q, dev, xs, frames, peaks):
     ach = frames * NQ * FLOP_PER_FRAME_STAGE / (ms * 1e-3) / 1e12
     out["trained_like"] = {"ms": ms, "frames_per_s": frames / (ms * 1e-3), "achieved": ach, "frac": ach / peaks["tflops"],
                            "certified_share": st["certified"] / max(1, st["searched"]), "rescored": st["rescored"],
-                           "fullscan": st["fullscan"], "fit": "k-means init (10 iterations) + 25 EMA training forwards on the bench latents"}
+                           "wide": st["wide"], "wide_candidates": st["wide_candidates"],
+                           "fullscan": st["fullscan"], "fit": "k-means init (10 iterations) + 25 EMA training forwards on the bench latents",
+                           "bound": "per-code score-error bound on the stages whose norms are heterogeneous (chosen by rvq_pack)"}
     out["train_forward"] = {"ms": t_train, "frames_per_s": frames / (t_train * 1e-3),
-                            "what": "steady-state training forward (search, quantized sum, commitment losses, expiry, EMA update)"}
+                            "what": "steady-state training forward on the fitted tables (search with the EMA statistics in the same launch, "
+                                    "quantized sum, commitment losses, EMA update, pack rebuild)"}
     ref = _reference_module()
     if ref is not None:
         ref = ref.to(dev)

@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   const bool tc = tc_shape(K, D);
   int Kp = 1; while (Kp < K) Kp <<= 1;
   float* norms = sh;                      // Kp
-  unsigned char* outl = (unsigned char*)(sh + Kp);   // K
+  unsigned long long* hashes = (unsigned long long*)(sh + Kp);   // K: 64-bit hash of every row (duplicate detection)
+  unsigned long long* tab_h = hashes + K;                        // 2 Kp: open-addressing table of the hashes ...
+  int* tab_i = (int*)(tab_h + 2 * Kp);                           // 2 Kp: ... and the lowest row index that carries each
+  unsigned char* outl = (unsigned char*)(tab_i + 2 * Kp);        // K
 
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
     float nv = __int_as_float(0x7f800000);
@@ -69,7 +72,14 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       // in the same order as before
       const float* col = tT + k;
       float acc = 0.f, amax = 0.f;
-      for (int d = 0; d < D; ++d) { float v = col[size_t(d) * K]; acc = fmaf(v, v, acc); amax = fmaxf(amax, fabsf(v)); }
+      unsigned h1 = 0x811c9dc5u, h2 = 0x9747b28cu;      // two 32-bit multiplicative hashes of the row's bit patterns
+      for (int d = 0; d < D; ++d) {
+        float v = col[size_t(d) * K]; acc = fmaf(v, v, acc); amax = fmaxf(amax, fabsf(v));
+        const unsigned bits = v == 0.f ? 0u : __float_as_uint(v);                   // (-0 and +0 are the same row element)
+        h1 = h1 * 31u + bits;
+        h2 = (h2 ^ bits) * 0x9e3779b1u;
+      }
+      hashes[k] = ((static_cast<unsigned long long>(h1) << 32) | h2) | 1ull;      // (0 marks an empty table slot)
       cn[k] = acc;
       nv = sqrtf(acc);
       // range flags for the fp16 image: B holds -2c, the augmented column holds |c|^2
@@ -77,8 +87,20 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     }
     norms[k] = nv;
   }
+  for (int i = threadIdx.x; i < 2 * Kp; i += blockDim.x) { tab_h[i] = 0ull; tab_i[i] = 0x7fffffff; }
   __syncthreads();
   if (!tc) return;
+  // lowest row index per distinct hash: insert with linear probing (at most K of the 2 Kp slots fill)
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const unsigned long long hk = hashes[k];
+    unsigned slot = unsigned(hk >> 20) & unsigned(2 * Kp - 1);
+    while (true) {
+      const unsigned long long prev = atomicCAS(&tab_h[slot], 0ull, hk);
+      if (prev == 0ull || prev == hk) { atomicMin(&tab_i[slot], k); break; }
+      slot = (slot + 1) & unsigned(2 * Kp - 1);
+    }
+  }
+  __syncthreads();
 
   // bitonic sort of the norms (ascending); +inf padding sinks to the end
   for (int size = 2; size <= Kp; size <<= 1) {
@@ -95,7 +117,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     }
   }
   __shared__ float s_thr, s_cref, s_cmin, s_outmin, s_cmax, s_db2, s_gmax, s_bmax, s_nlow;
-  __shared__ int s_nout;
+  __shared__ int s_nout, s_nalias;
   if (threadIdx.x == 0) {
     // reference norm for the outlier test: a high quantile (15/16), not the median -- a codebook whose norms are bimodal
     // with the large group in the minority (e.g. the first EMA steps after a k-means init, where most rows have shrunk) must
@@ -104,7 +126,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     s_thr = kOutlierMul * ref;
     s_cmin = norms[0];
     s_cmax = norms[K - 1];
-    s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0; s_db2 = 0.f; s_gmax = 0.f; s_bmax = 0.f;
+    s_cref = 0.f; s_outmin = __int_as_float(0x7f800000); s_nout = 0; s_nalias = 0; s_db2 = 0.f; s_gmax = 0.f; s_bmax = 0.f;
     s_nlow = norms[K / 64];                // a low quantile of the norms (the K/64 smallest codes are at or below it)
   }
   __syncthreads();
@@ -113,13 +135,31 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     float lcref = 0.f, loutmin = __int_as_float(0x7f800000), ldb2 = 0.f, lgmax = 0.f, lbmax = 0.f; int lnout = 0;
     float2* gab = const_cast<float2*>(pv.gab(s));
     __half* g16 = const_cast<__half*>(pv.g16(s, K));
+    int lnalias = 0;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       float nv = sqrtf(cn[k]);
       bool o = outl[k] || !(nv <= s_thr);
-      outl[k] = o ? 1 : 0;
+      // An exact duplicate of a row with a lower index can never win (equal distances, ties go to the lowest index,
+      // core_vq.py:188): it leaves the image like an outlier does, so that a crowd of identical rows (zero residuals drawn as
+      // k-means means, silence) does not put the whole crowd into every candidate set.  (The exact scans still see it.)
+      bool alias = false;
+      if (!o) {
+        // first row with the same hash (table look-up), then one element-wise check
+        const unsigned long long hk = hashes[k];
+        unsigned slot = unsigned(hk >> 20) & unsigned(2 * Kp - 1);
+        while (tab_h[slot] != hk) slot = (slot + 1) & unsigned(2 * Kp - 1);
+        const int first = tab_i[slot];
+        if (first < k) {
+          bool same = true;
+          for (int d = 0; d < D && same; ++d) same = tT[size_t(d) * K + first] == tT[size_t(d) * K + k];
+          alias = same;
+        }
+      }
+      outl[k] = (o || alias) ? 1 : 0;
       float2 ab = make_float2(0.f, 0.f);
       __half gh = __float2half_rn(0.f);
       if (o) { loutmin = fminf(loutmin, nv); ++lnout; }
+      else if (alias) ++lnalias;
       else {
         lcref = fmaxf(lcref, nv);
         // exact rounding residue of this code's fp16 operand row (-2c): |b - fp16(b)|^2
@@ -147,6 +187,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     atomicMax((int*)&s_bmax, __float_as_int(lbmax));
     atomicMin((int*)&s_outmin, __float_as_int(loutmin));
     atomicAdd(&s_nout, lnout);
+    atomicAdd(&s_nalias, lnalias);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -172,7 +213,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     // |x| bound under which (a) outlier codes provably lose to the smallest-norm code and
     // (b) every live score + margin stays below the outlier score, (c) x fits fp16.
     float xl = 6.0e4f;
-    if (s_nout > 0) {
+    if (s_nout + s_nalias > 0) {     // (no outlier by norm: s_outmin = +inf and the first clause is void)
       xl = fminf(xl, 0.5f * (s_outmin - s_cmin));
       float denom = 2.f * s_cmin + (m.margin_coef + m.margin_dr * kHalfUlp * 1.01f) + 1e-30f;   // |dr| <= 2^-11 |r| (+ subnormals)
       xl = fminf(xl, (0.9f * kBigScore - s_cmin * s_cmin) / denom);
@@ -225,7 +266,7 @@ __global__ void __launch_bounds__(256) pack_image_kernel(unsigned char* pack, in
 
 int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st) {
   int Kp = 1; while (Kp < K) Kp <<= 1;
-  size_t meta_smem = size_t(Kp) * 4 + size_t(K);
+  size_t meta_smem = size_t(Kp) * 4 + size_t(K) * 9 + size_t(Kp) * 24;
   RVQ_REQUIRE(meta_smem <= 200 * 1024, "rvq_pack: codebook_size %d too large", K);
   RVQ_CUDA(cudaFuncSetAttribute(pack_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta_smem));
   RVQ_CUDA(cudaMemsetAsync(pack, 0, kHeaderBytes, st));
@@ -820,6 +861,42 @@ __global__ void kmeans_scatter_kernel(const float* __restrict__ samples, int64_t
   }
 }
 
+// D == 128: a warp walks a run of consecutive samples, lane = 16-byte chunk of the row, and keeps the running sum of the
+// current bucket in registers; it is flushed (one red.global.add.v4.f32 per lane + one count) when the bucket changes.
+// Lloyd iterations on residuals routinely produce a giant cluster (tens of thousands of samples on one mean): one scalar
+// atomic per element then serialises 40 000 adds on each of its 128 addresses (0.5-1 ms per iteration, measured); runs of
+// equal buckets collapse here, and every flush is a quarter of the instructions.
+constexpr int kKmRun = 32;
+__global__ void __launch_bounds__(256) kmeans_scatter128_kernel(const float* __restrict__ samples, int64_t N,
+                                                                const int64_t* __restrict__ buckets, int K,
+                                                                float* sums, unsigned long long* bins) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n0 = warp * kKmRun;
+  if (n0 >= N) return;
+  const int64_t n1 = n0 + kKmRun < N ? n0 + kKmRun : N;
+  // the run's buckets: one per lane, handed round with shuffles
+  const int64_t kb = n0 + lane < n1 ? buckets[n0 + lane] : -1;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = -1, cnt = 0;
+  auto flush = [&]() {
+    if (cur >= 0 && cnt > 0) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(sums + size_t(cur) * 128 + 4 * lane), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+      if (lane == 0) atomicAdd(&bins[cur], (unsigned long long)cnt);
+    }
+  };
+  for (int i = 0; i < int(n1 - n0); ++i) {
+    const int64_t k64 = __shfl_sync(0xffffffffu, kb, i);
+    const int k = (k64 < 0 || k64 >= K) ? -1 : int(k64);
+    if (k != cur) { flush(); cur = k; cnt = 0; acc = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (k >= 0) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(samples + (n0 + i) * 128) + lane);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; ++cnt;
+    }
+  }
+  flush();
+}
+
 __global__ void kmeans_finalize_kernel(float* means, const float* __restrict__ sums,
                                        const unsigned long long* __restrict__ bins, int K, int D) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -988,7 +1065,12 @@ int rvq_kmeans_update(const float* samples, int64_t N, int D, const int64_t* buc
   RVQ_CUDA(cudaMemsetAsync(bins, 0, size_t(K) * 8, st));
   RVQ_CUDA(cudaMemsetAsync(sums, 0, size_t(K) * D * 4, st));
   if (N > 0) {
-    kmeans_scatter_kernel<<<chain_grid(N), 256, 0, st>>>(samples, N, D, buckets, K, sums, (unsigned long long*)bins);
+    if (D == 128 && (reinterpret_cast<uintptr_t>(samples) & 15) == 0 && (reinterpret_cast<uintptr_t>(sums) & 15) == 0) {
+      const int64_t warps = (N + kKmRun - 1) / kKmRun;
+      kmeans_scatter128_kernel<<<unsigned((warps + 7) / 8), 256, 0, st>>>(samples, N, buckets, K, sums, (unsigned long long*)bins);
+    } else {
+      kmeans_scatter_kernel<<<chain_grid(N), 256, 0, st>>>(samples, N, D, buckets, K, sums, (unsigned long long*)bins);
+    }
     RVQ_LAUNCH_CHECK("kmeans_scatter_kernel");
   }
   int n = K * D;

@@ -57,6 +57,57 @@ def sample_vectors(samples: torch.Tensor, num: int) -> torch.Tensor:
     return samples[sample_indices(samples.shape[0], num, samples.device)]
 
 
+class _LloydGraph:
+    """One Lloyd iteration (pack, assign, scatter / finalise) on fixed buffers, captured once into a CUDA graph and replayed.
+    The buffers belong to the graph: a call copies its samples and starting means in and the result out, so one graph serves
+    every k-means of the same shape (the stages of a stack, later calls).  Capturing a fresh graph per call cost 2-60 ms each
+    (growing with the number of graphs the process had made) against 5 ms for the 49 replays of a stage."""
+
+    def __init__(self, n: int, k: int, d: int, device: torch.device):
+        self.samples = torch.empty((n, d), dtype=torch.float32, device=device)
+        self.means = torch.empty((k, d), dtype=torch.float32, device=device)
+        self.graph: tp.Optional[torch.cuda.CUDAGraph] = None
+        self.bins: tp.Optional[torch.Tensor] = None
+
+    def step(self) -> torch.Tensor:
+        pk = ops.pack([self.means])
+        buckets = ops.kmeans_assign(pk, self.samples)
+        return ops.kmeans_update(self.samples, buckets, self.means)
+
+    def run(self, num_iters: int) -> torch.Tensor:
+        if num_iters <= 0:
+            return torch.zeros(self.means.shape[0], dtype=torch.int64, device=self.means.device)
+        if torch.cuda.is_current_stream_capturing():     # already inside somebody's capture: plain launches (same kernels)
+            for _ in range(num_iters):
+                bins = self.step()
+            return bins
+        if self.graph is None:
+            # the first iteration runs eagerly (it also pays the one-time function-attribute calls), the second is captured
+            bins = self.step()
+            num_iters -= 1
+            if num_iters == 0:
+                return bins
+            # (the debug counters of rvq_search_counters are a per-thread pointer the launches read: a captured launch would
+            # keep it beyond the life of the caller's buffer, so the capture runs with the counters off)
+            L.check(L.load().rvq_search_counters(None), "rvq_search_counters")
+            graph = torch.cuda.CUDAGraph()
+            dev = self.means.device
+            cur, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):           # (the raw capture API: torch.cuda.graph() would add a gc.collect per call)
+                graph.capture_begin()
+                self.bins = self.step()
+                graph.capture_end()
+            cur.wait_stream(side)
+            self.graph = graph
+        for _ in range(num_iters):
+            self.graph.replay()
+        return self.bins.clone()
+
+
+_lloyd_graphs: tp.Dict[tp.Tuple[int, int, int, int], _LloydGraph] = {}
+
+
 def kmeans(samples: torch.Tensor, num_clusters: int, num_iters: int = 10,
            init_means: tp.Optional[torch.Tensor] = None) -> tp.Tuple[torch.Tensor, torch.Tensor]:
     """core_vq.py:80-102: Lloyd iterations on flat ``[N, D]`` samples.  Assignment (direct
@@ -64,39 +115,18 @@ def kmeans(samples: torch.Tensor, num_clusters: int, num_iters: int = 10,
     update (empty clusters keep their mean) are the ``rvq_kmeans_*`` kernels.  ``init_means``
     lets a caller inject the starting centroids instead of drawing them."""
     L.require_cuda_f32(samples, "kmeans samples")
-    samples = samples.contiguous()
-    means = (sample_vectors(samples, num_clusters) if init_means is None else init_means).contiguous().clone()
-    bins = torch.zeros(num_clusters, dtype=torch.int64, device=samples.device)
-
-    def lloyd_step() -> torch.Tensor:
-        pk = ops.pack([means])
-        buckets = ops.kmeans_assign(pk, samples)
-        return ops.kmeans_update(samples, buckets, means)
-
-    if num_iters < 4:
-        for _ in range(num_iters):
-            bins = lloyd_step()
-        return means, bins
-    # A Lloyd iteration is three short launches (pack, assign, scatter / finalise) on fixed buffers: the first one runs
-    # eagerly (it also pays the one-time function-attribute calls), the second is captured into a CUDA graph and the graph
-    # is replayed for the remaining iterations, which removes the host launch gaps (~60 % of an iteration).
-    bins = lloyd_step()
-    if torch.cuda.is_current_stream_capturing():     # already inside somebody's capture: plain launches (same kernels)
-        for _ in range(num_iters - 1):
-            bins = lloyd_step()
-        return means, bins
-    graph = torch.cuda.CUDAGraph()
-    cur, side = torch.cuda.current_stream(samples.device), torch.cuda.Stream(samples.device)
-    side.wait_stream(cur)
-    with torch.cuda.stream(side):               # (the raw capture API: torch.cuda.graph() would add a gc.collect per stage)
-        graph.capture_begin()
-        gbins = lloyd_step()
-        graph.capture_end()
-    cur.wait_stream(side)
-    for _ in range(num_iters - 1):
-        graph.replay()
-    bins = gbins.clone()
-    return means, bins
+    means0 = sample_vectors(samples, num_clusters) if init_means is None else init_means
+    n, d = (int(v) for v in samples.shape)
+    dev = samples.device
+    key = (n, int(num_clusters), d, dev.index if dev.index is not None else torch.cuda.current_device())
+    lg = _lloyd_graphs.get(key)
+    if lg is None:
+        _lloyd_graphs.clear()                     # one shape at a time: the buffers of an old shape are released
+        lg = _lloyd_graphs[key] = _LloydGraph(n, int(num_clusters), d, dev)
+    lg.samples.copy_(samples)
+    lg.means.copy_(means0)
+    bins = lg.run(num_iters)
+    return lg.means.clone(), bins
 
 
 def _flat_as_bdt(flat: torch.Tensor) -> torch.Tensor:

@@ -13,8 +13,11 @@ with warnings.catch_warnings():
             q(sweep.latents(64, 750, 500 + i, dev), 75, 24.0)
 q.eval()
 x = sweep.latents(64, 750, 900, dev)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()          # ncu --profile-from-start off: only the eval encodes below are captured
 with torch.no_grad():
     for _ in range(5):
         c = q.encode(x, 75, 24.0)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", int(c.sum()))

@@ -1,1 +1,2 @@
-VARIANTS="prev:-@rvq_tc_prev.cu cur:- nocnt:RVQ_NO_WIDE_COUNTERS owner:RVQ_WIDE_OWNER both:RVQ_NO_WIDE_COUNTERS,RVQ_WIDE_OWNER" bash scripts/run_variants.sh
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python scripts/time_kmeans_repeat.py 2>&1 | tail -6

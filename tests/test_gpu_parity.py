@@ -100,8 +100,13 @@ def test_ties_wide_candidate_sets_and_non_finite_frames():
     q = build_module(case).eval()
     with torch.no_grad():
         e0 = q.vq.layers[0]._codebook.embed
+        e0[0, 5] = 0.0
         for dst in (33, 66, 99, 132, 165, 700):          # six copies of row 0 in different batches and classes
             e0[dst] = e0[0]
+        e0[700, 5] = -0.0                                # ... one of them with a zero of the other sign: still the same row
+                                                         # (exact duplicates leave the search image at pack time: only the
+                                                         # lowest index can win, core_vq.py:188)
+        e0[800] = e0[0]; e0[800, 17] = torch.nextafter(e0[0, 17].cpu(), torch.tensor(9.0)).item()   # a near-duplicate does not
         e0[901] = e0[5]                                  # a plain pair
         e2 = q.vq.layers[2]._codebook.embed
         e2[512:520] = e2[3]                              # eight copies inside one batch
