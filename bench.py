@@ -32,7 +32,7 @@ FLOP_PER_FRAME_STAGE = 2 * BINS * D          # only the x.c^T co
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_encode_kernel launch at cfg2, from the committed ncu --set full
 # capture named below (NOT measured by this run: ncu replays kernels, a bench run must not sit under it).  Algorithmic:
 # 24.6 MB latents + 12.3 MB codes; the capture also sees the first touch of the 43 MB pack, which then stays in L2.
-NCU_TRAFFIC_FILE = "profiles/r2p_tc_encode_ncu_raw.csv"
+NCU_TRAFFIC_FILE = "profiles/r2q_tc_encode_ncu_raw.csv"
 
 
 def _ncu_traffic():

@@ -1,6 +1,6 @@
 # final measurement set of round 2 on one B200: tests, smoke, bench (+ reference arm), sweep, ncu full capture of the search,
 # launch lists of the bench and of the training forward
-TAG=${TAG:-r2p}
+TAG=${TAG:-r2q}
 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/${TAG}_tests.log
 python __graft_entry__.py --smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${TAG}_smoke.log
 python scripts/prof_encode.py > gpurun_out/${TAG}_prof_plain.log 2>&1 || exit 1
