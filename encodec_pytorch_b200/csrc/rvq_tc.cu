@@ -9,9 +9,11 @@
 //
 //   scores   S[f,k] = -2 r_f . c_k + |c_k|^2 from tcgen05.mma kind::f16 (fp32 accumulation in tensor memory),
 //            M=128 frames, N=128 codes per chunk, 9 K-steps of 16:
-//            A = fp16(r), held IN TENSOR MEMORY (64 columns per slot; K-steps 0..7) + one constant shared-memory
-//                block whose columns 128,129 = 1 (K-step 8: picks up the hi/lo halves of |c|^2);
-//            B = fp16 image of the codebook (cols 0..127 = -2c, cols 128,129 = hi/lo of |c|^2), streamed by the
+//            A = fp16(r), held IN TENSOR MEMORY (64 columns per slot; K-steps 0..7) + one shared-memory block per slot
+//                whose columns 128,129 = 1 (K-step 8: picks up the hi/lo halves of |c|^2) and whose columns 130 / 132
+//                carry the frame's bound R >= |r| when the stage certifies with the per-code bound (else 0);
+//            B = fp16 image of the codebook (cols 0..127 = -2c, cols 128,129 = hi/lo of |c|^2, cols 130,132 = -g16_k,
+//                the code's own error coefficient: the accumulator then holds LOWER BOUNDS of the true scores), streamed by the
 //                TMA engine (cp.async.bulk) from the L2-resident pack into a ring of 7 third-of-a-chunk
 //                slots (6 K-groups = 12 KB each; small slots keep more bytes in flight than whole chunks would);
 //            D = 3 accumulator buffers of 128 TMEM columns shared by both slots.
@@ -23,7 +25,7 @@
 //                   warp applies r <- r - q itself); (3) r - q in registers -> fp16 operand of the next stage to tensor
 //                   memory (one tcgen05.st.16x256b.x8) -> a_ready; (4) off the chain: residual rows back to shared
 //                   memory, exact rounding residue of the operand, squared error -> dr_ready; tile loads;
-//            12  TMA producer;  13..15  MMA issuers, chunks round-robin (13 owns the TMEM allocation).
+//            12  TMA producer;  13  MMA issuer (owns the TMEM allocation);  14, 15 idle.
 //            setmaxnreg: 152 registers for the score warps, 160 for the update warps, 40 for the last warpgroup.
 //   sync     mbarriers only between roles: a_ready[slot] (update -> MMA), acc_full/acc_empty (MMA <-> score),
 //            cand_ready[slot] (score -> update), dr_ready[slot] (update -> score), full/empty (TMA <-> MMA).
@@ -32,8 +34,12 @@
 // (code mod 32).  A code is within `delta` of the minimum iff its batch AND its class are; delta bounds the fp16
 // score error two-sidedly (rvq_common.cuh, StageMeta), so the exact fp32 winner is certified when exactly one batch
 // and one class qualify.  Otherwise the candidates (flagged batches x flagged classes) are re-scored in fp32 with
-// the reference's formula (core_vq.py:181-189, ties -> lowest index).  Frames outside the fp16 image's validity
-// range take an exact fp32 scan.
+// the reference's formula (core_vq.py:181-189, ties -> lowest index): 2..4 candidates by one warp per frame, wider sets by
+// all update warps together.  Frames outside the fp16 image's validity range take an exact fp32 scan.  Two bounds, both
+// rigorous (rvq_common.cuh, StageMeta): per stage (set by the largest code) and per code (the threshold comes from the
+// coefficients of the code that attains the minimum; tables with heterogeneous norms, i.e. fitted ones); stages pick at pack
+// time, and the kernel runs the specialisation of its body that matches the call (tc_encode_body<TRAIN, PC>).
+// The training variant also accumulates the EMA statistics of core_vq.py:227-228 (rvq_encode_train).
 #include "rvq_common.cuh"
 #include "rvq_ptx.cuh"
 

@@ -1,2 +1,1 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python scripts/time_kmeans_repeat.py 2>&1 | tail -6
+VARIANTS="cur:- pref:RVQ_SCORE_PREFETCH cur2:- pref2:RVQ_SCORE_PREFETCH" bash scripts/run_variants.sh
