@@ -1,1 +1,1 @@
-VARIANTS="cur:- pref:RVQ_SCORE_PREFETCH cur2:- pref2:RVQ_SCORE_PREFETCH" bash scripts/run_variants.sh
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "ties or more_than_32" 2>&1 | tail -15

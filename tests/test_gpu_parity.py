@@ -93,9 +93,17 @@ def test_both_search_paths_agree_with_oracle(force_exact):
     assert torch.equal(r, res)
 
 
-def test_ties_wide_candidate_sets_and_non_finite_frames():
+@pytest.mark.parametrize("mode", [0, 1])
+def test_ties_wide_candidate_sets_and_non_finite_frames(mode):
     """Exact ties (duplicated code rows -> lowest index, core_vq.py:188), candidate sets too wide for the
-    prefetched re-score (mask enumeration), and NaN / inf frames (exact scan, NaN-propagating argmax)."""
+    prefetched re-score (mask enumeration), and NaN / inf frames (exact scan, NaN-propagating argmax); under the default
+    choice of the score-error bound and with the per-code bound forced on every stage."""
+    from encodec_pytorch_b200 import _ops as _o
+    with _o.pack_bound_mode(mode):
+        _ties_body()
+
+
+def _ties_body():
     case = C.Case("ties", 3, 128, 150, 1024, 6, 75, None, 808, 11)
     q = build_module(case).eval()
     with torch.no_grad():
@@ -171,6 +179,34 @@ def test_degenerate_tables_hundreds_of_candidates(mode):
     assert st["bad"] == 0 and st["near_tie"] <= 0.02 * st["pairs"], st
     c = counters.read()
     assert c["wide"] > 100 and c["wide_candidates"] > 30 * c["wide"], c
+
+
+def test_more_than_32_stages_and_mixed_bounds():
+    """A 40-stage stack (the pack is built 32 stages at a time, the kernel gathers the per-code switches of up to 64
+    stages) whose stages alternate between uniform and heterogeneous norms, so that both bounds and the hand-over of the
+    frame's norm bound between them are exercised inside one launch; also a call that starts in the middle of the stack."""
+    from encodec_pytorch_b200 import _ops as ops
+    case = C.Case("deep", 3, 128, 211, 1024, 40, 75, None, 606, 31)
+    q = build_module(case).eval()
+    with torch.no_grad():
+        for i in range(0, 40, 3):                              # every third stage: a third of the rows shrunk 20x
+            q.vq.layers[i]._codebook.embed[::3] *= 0.05
+    q.vq.invalidate()
+    states = module_states(q)
+    x = C.latents(case.b, case.d, case.t, case.x_seed)
+    with torch.no_grad():
+        codes = q.encode(x.cuda(), 75)
+    assert codes.shape[0] == 40
+    st = O.compare_codes_teacher_forced(states, x, codes.cpu())
+    assert st["bad"] == 0 and st["near_tie"] <= max(2, 2e-3 * st["pairs"]), st
+    pk = q.vq._stack_pack()
+    part, _, _, _ = ops.encode(pk, x.cuda(), 0, 7)           # the first 7 stages alone give the same codes (frames' chains are causal)
+    assert torch.equal(part, codes[:7])
+    # stages 33..39 applied to the residual left by the first 33
+    res33 = x - O.rvq_decode(states[:33], codes[:33].cpu())
+    tail, _, _, _ = ops.encode(pk, res33.cuda(), 33, 7)
+    st2 = O.compare_codes_teacher_forced(states[33:], res33, tail.cpu())
+    assert st2["bad"] == 0, st2
 
 
 def test_fused_ema_statistics_match_the_statistics_pass():
