@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   const bool tc = tc_shape(K, D);
   int Kp = 1; while (Kp < K) Kp <<= 1;
   float* norms = sh;                      // Kp
+  // (the three arrays below exist only for shapes the tensor-core search serves: simt_pack sizes the block's memory)
   unsigned long long* hashes = (unsigned long long*)(sh + Kp);   // K: 64-bit hash of every row (duplicate detection)
   unsigned long long* tab_h = hashes + K;                        // 2 Kp: open-addressing table of the hashes ...
   int* tab_i = (int*)(tab_h + 2 * Kp);                           // 2 Kp: ... and the lowest row index that carries each
-  unsigned char* outl = (unsigned char*)(tab_i + 2 * Kp);        // K
+  unsigned char* outl = tc ? (unsigned char*)(tab_i + 2 * Kp) : (unsigned char*)(sh + Kp);   // K
 
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
     float nv = __int_as_float(0x7f800000);
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
         h1 = h1 * 31u + bits;
         h2 = (h2 ^ bits) * 0x9e3779b1u;
       }
-      hashes[k] = ((static_cast<unsigned long long>(h1) << 32) | h2) | 1ull;      // (0 marks an empty table slot)
+      if (tc) hashes[k] = ((static_cast<unsigned long long>(h1) << 32) | h2) | 1ull;      // (0 marks an empty table slot)
       cn[k] = acc;
       nv = sqrtf(acc);
       // range flags for the fp16 image: B holds -2c, the augmented column holds |c|^2
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
     }
     norms[k] = nv;
   }
-  for (int i = threadIdx.x; i < 2 * Kp; i += blockDim.x) { tab_h[i] = 0ull; tab_i[i] = 0x7fffffff; }
+  if (tc)
+    for (int i = threadIdx.x; i < 2 * Kp; i += blockDim.x) { tab_h[i] = 0ull; tab_i[i] = 0x7fffffff; }
   __syncthreads();
   if (!tc) return;
   // lowest row index per distinct hash: insert with linear probing (at most K of the 2 Kp slots fill)
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(256) pack_image_kernel(unsigned char* pack, in
 
 int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st) {
   int Kp = 1; while (Kp < K) Kp <<= 1;
-  size_t meta_smem = size_t(Kp) * 4 + size_t(K) * 9 + size_t(Kp) * 24;
+  size_t meta_smem = size_t(Kp) * 4 + size_t(K) + (tc_shape(K, D) ? size_t(K) * 8 + size_t(Kp) * 24 : 0);
   RVQ_REQUIRE(meta_smem <= 200 * 1024, "rvq_pack: codebook_size %d too large", K);
   RVQ_CUDA(cudaFuncSetAttribute(pack_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta_smem));
   RVQ_CUDA(cudaMemsetAsync(pack, 0, kHeaderBytes, st));

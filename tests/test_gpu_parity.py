@@ -209,6 +209,33 @@ def test_more_than_32_stages_and_mixed_bounds():
     assert st2["bad"] == 0, st2
 
 
+@pytest.mark.parametrize("d,k", [(32, 4096), (128, 2048), (64, 1000)])
+def test_other_shapes_take_the_fp32_search(d, k):
+    """Shapes outside the tensor-core search (K > 1024, D != 128, K not a multiple of 128): pack, fp32 search, decode and a
+    training forward against the oracle."""
+    case = C.Case(f"shape_d{d}_k{k}", 2, d, 90, k, 3, 75, None, 515, 41)
+    q = build_module(case).eval()
+    states = module_states(q)
+    x = C.latents(case.b, case.d, case.t, case.x_seed)
+    with torch.no_grad():
+        codes = q.encode(x.cuda(), 75)
+        dec = q.decode(codes)
+    assert_codes_match(states, x, codes, O.rvq_encode(states, x).numpy())
+    assert torch.equal(dec.cpu(), O.rvq_decode(states, codes.cpu()))
+    q.train()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.no_grad():
+            res = q(x.cuda(), 75)
+    st = O.compare_codes_teacher_forced(states, x, res.codes.cpu())
+    assert st["bad"] == 0, st
+    for i in range(3):
+        idx = res.codes[i].reshape(-1).cpu()
+        cs = states[i]["cluster_size"] * 0.99 + torch.bincount(idx, minlength=k).float() * 0.01
+        torch.testing.assert_close(q.vq.layers[i]._codebook.cluster_size.cpu(), cs, rtol=1e-5, atol=1e-6)
+
+
 def test_fused_ema_statistics_match_the_statistics_pass():
     """rvq_encode_train: the EMA statistics the search accumulates itself (core_vq.py:227-228) against rvq_ema_stats run on
     the same codes, and against a bincount / index_add of the oracle's residual chain (ragged frame count: padded tile
