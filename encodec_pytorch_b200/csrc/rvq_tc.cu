@@ -38,7 +38,7 @@
 // all update warps together.  Frames outside the fp16 image's validity range take an exact fp32 scan.  Two bounds, both
 // rigorous (rvq_common.cuh, StageMeta): per stage (set by the largest code) and per code (the threshold comes from the
 // coefficients of the code that attains the minimum; tables with heterogeneous norms, i.e. fitted ones); stages pick at pack
-// time, and the kernel runs the specialisation of its body that matches the call (tc_encode_body<TRAIN, PC>).
+// time, and the kernel runs the specialisation of its body that matches the call (tc_encode_body<TRAIN, PC, STE>).
 // The training variant also accumulates the EMA statistics of core_vq.py:227-228 (rvq_encode_train).
 #include "rvq_common.cuh"
 #include "rvq_ptx.cuh"
@@ -291,18 +291,11 @@ __device__ __forceinline__ float dot_row(const Row4& a, const Row4& b) {
 // rounding residue |r - fp16(r)|^2 of the new residual (it enters the score-error margin of the next stage) and
 // the squared-error partial.  Called by whole quarter-warps (8 converged lanes; all lanes of the warp shuffle).
 // new residual n = r - q (core_vq.py:364 / :348; straight-through arithmetic of :309 in training)
-template <bool TRAIN>
-__device__ __forceinline__ float4 sub_row(const TcParams& p, const float4& rv, float4 q) {
-  if (TRAIN && p.ste) { q.x = rv.x + (q.x - rv.x); q.y = rv.y + (q.y - rv.y); q.z = rv.z + (q.z - rv.z); q.w = rv.w + (q.w - rv.w); }
+template <bool STE>
+__device__ __forceinline__ float4 sub_row(const float4& rv, float4 q) {
+  if (STE) { q.x = rv.x + (q.x - rv.x); q.y = rv.y + (q.y - rv.y); q.z = rv.z + (q.z - rv.z); q.w = rv.w + (q.w - rv.w); }
   return make_float4(rv.x - q.x, rv.y - q.y, rv.z - q.z, rv.w - q.w);
 }
-// exact fp32 r <- r - q for a frame at an arbitrary position (candidate-list / wide paths)
-template <bool TRAIN>
-__device__ __forceinline__ void apply_row(const TcParams& p, float* rs, int f, int j, const Row4& r, const Row4& qrow) {
-  #pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(rs + rs_off(f, 8 * i + j)) = sub_row<TRAIN>(p, r.v[i], qrow.v[i]);
-}
-
 // A frame whose flagged batches x flagged classes give more than 4 candidates: the whole warp works on it,
 // 8 candidates per step (2 per quarter-warp); the quarter that found the winner updates the frame.
 template <int NC> struct Cand { int c[NC]; Row4 w[NC]; float nrm[NC]; };
@@ -399,7 +392,7 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
 //      residue, and the 16 frames x 64 columns of the next stage's operand go to tensor memory with ONE
 //      tcgen05.st.16x256b.x8 -- the register layout of that shape is exactly this lane/chunk assignment, so no
 //      transposition pass and no second barrier are needed.
-template <bool TRAIN>
+template <bool TRAIN, bool STE>
 __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsigned char* ms, int u, int lane, int s, int rot,
                                             int nchunks, int64_t tile_n0, const float* __restrict__ t32,
                                             const float* __restrict__ cn, uint32_t taddr, bool store, uint32_t bar_a, float& sq,
@@ -486,7 +479,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     const int64_t nfr = tile_n0 + it.f;
     if (it.ck == bcode) {                                        // the winner's quarter holds its row: r <- r - q
       #pragma unroll
-      for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(rs + rs_off(it.f, 8 * k + j)) = sub_row<TRAIN>(p, it.rl[k], it.w[k]);
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(rs + rs_off(it.f, 8 * k + j)) = sub_row<STE>(it.rl[k], it.w[k]);
       if (TRAIN && p.ema_sum != nullptr && it.f < p.tf && nfr < p.N) {      // EMA statistics: embed_sum[code] += r, counts[code] += 1
         float* row = p.ema_sum + (size_t(s) * p.K + bcode) * 128 + 4 * j;
         #pragma unroll
@@ -570,7 +563,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
     for (int i = 0; i < 8; ++i) {
       const float4 rv = *reinterpret_cast<const float4*>(rbase + ((i ^ (sw >> 2)) << 4));
       if (TRAIN && stats) red_add_f4(srow + 16 * i, rv);
-      const float4 n = done ? rv : sub_row<TRAIN>(p, rv, qr[i]);
+      const float4 n = done ? rv : sub_row<STE>(rv, qr[i]);
       qr[i] = n;
       w[4 * i + 2 * half] = pack_half2(n.x, n.y);
       w[4 * i + 2 * half + 1] = pack_half2(n.z, n.w);
@@ -623,7 +616,7 @@ __device__ __forceinline__ void update_pass(const TcParams& p, float* rs, unsign
 // PC: some stage of the call certifies with the per-code bound (StageMeta::percode; bit s of pcmask = stage stage0 + s).  The
 // kernel picks the specialisation at its top, so a stack on the per-stage bound runs code that does not contain the per-code
 // branch at all (its mere presence in the winner phase cost 1.8 % at cfg2).
-template <bool TRAIN, bool PC>
+template <bool TRAIN, bool PC, bool STE>
 __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned long long pcmask) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -837,7 +830,7 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
           if ((s + 4 == p.n_q || (p.n_q < 4 && s == 0)) && (jt + 1) * p.n_q < (X ? steps1 : steps0)) prefetch_tile(tile0 + X + 2 * (jt + 1));
           float sq = 0.f;
           // operand rows of this warp: TMEM lanes 32q + 16h .. +15, columns of slot X
-          update_pass<TRAIN>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st),
+          update_pass<TRAIN, STE>(p, rs, ms, u, lane, s, rot, nchunks, tile_n0, pv.tab32(st), pv.cnorm(st),
                              tmem + (uint32_t(q * 32 + h * 16) << 16) + kTmemA + 64 * X, !last, RVQ_BAR(a_ready, X), sq, X, n,
 #ifdef RVQ_TC_TRACE
                              t_kernel0
@@ -1124,8 +1117,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
 #ifdef RVQ_NO_PERCODE      // A/B builds: the per-code branch switched off
   pcmask = 0ull;
 #endif
-  if (pcmask != 0ull) tc_encode_body<TRAIN, true>(p, pcmask);
-  else tc_encode_body<TRAIN, false>(p, 0ull);
+  // (the straight-through arithmetic of core_vq.py:309 is a compile-time property of the body too: as a run-time switch
+  // inside the residual update it cost the training call 3 %)
+  if (TRAIN && p.ste) {
+    if (pcmask != 0ull) tc_encode_body<TRAIN, true, TRAIN>(p, pcmask);
+    else tc_encode_body<TRAIN, false, TRAIN>(p, 0ull);
+  } else {
+    if (pcmask != 0ull) tc_encode_body<TRAIN, true, false>(p, pcmask);
+    else tc_encode_body<TRAIN, false, false>(p, 0ull);
+  }
 }
 
 int tc_debug_trace(long long* out_host, int n) {

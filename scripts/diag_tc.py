@@ -35,6 +35,9 @@ for nq in sorted({1, 8, NQ}):
     print(f"n_q={nq}: tc {t_tc:.3f} ms ({t_tc*1e-3*1.965e9/ (-(-tiles//ctas)*nq):.0f} cyc per tile-stage of the longest CTA), "
           f"certified {st['certified']}/{st['searched']}, rescored {st['rescored']}, fullscan {st['fullscan']}, mismatches vs exact {(c1 != c2).sum().item()}, sm clock {clk['sm_mhz']} MHz {clk['reasons']}")
 # the training variant of the kernel (straight-through arithmetic, loss numerators): which option costs what
-for name, kw in (("ste+sqerr", dict(want_sqerr=True, flags=L.FLAG_STE)), ("ste only", dict(flags=L.FLAG_STE)), ("sqerr only", dict(want_sqerr=True))):
+stats = ops.ema_stats_buffer(NQ, pk.K, pk.D, x.device)
+for name, kw in (("ste+sqerr", dict(want_sqerr=True, flags=L.FLAG_STE)), ("ste only", dict(flags=L.FLAG_STE)), ("sqerr only", dict(want_sqerr=True)),
+                 ("residual only", dict(want_residual=True)), ("stats only", dict(ema_stats_out=stats)),
+                 ("full training call", dict(want_sqerr=True, want_residual=True, flags=L.FLAG_STE, ema_stats_out=stats))):
     t = timed(lambda: ops.encode(pk, x, 0, NQ, **kw), n=50)
     print(f"train variant, {name}: {t:.3f} ms")
