@@ -1,3 +1,1 @@
-VARIANTS="cur:-" bash scripts/run_variants.sh
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python scripts/time_train_fitted.py 2>&1 | head -2
+VARIANTS="cur:- l1:RVQ_L1_PREFETCH cur2:- l12:RVQ_L1_PREFETCH" bash scripts/run_variants.sh 2>&1 | grep -v "train variant"
