@@ -339,16 +339,8 @@ __device__ __forceinline__ void resolve_wide(const TcParams& p, const float* rs,
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_cmask + f * 4);
   const uint32_t bm = *reinterpret_cast<const uint32_t*>(ms + Sm::m_bmask + f * 4);
   const int nc = __popc(cm), total = nc * __popc(bm);
-#ifndef RVQ_WIDE_KPER
-#define RVQ_WIDE_KPER 4
-#endif
-  constexpr int kPer = RVQ_WIDE_KPER;                      // candidates per quarter-warp and step
-#ifdef RVQ_WIDE_OWNER      // A/B builds: the frame's first warp alone
-  if (u != 0) return;
-  constexpr int kCoop = 1;
-#else
-  constexpr int kCoop = kUpdWarps;
-#endif
+  constexpr int kPer = 4;                                  // candidates per quarter-warp and step
+  constexpr int kCoop = kUpdWarps;                         // warps that share a frame's candidates
   if (4 * kPer * u >= total) return;                       // (warp-uniform) no candidate left for this warp
   const int w = 4 * u + qq;                                // this quarter's number among the 32 of the update warps
   // lane L: position of the L-th flagged batch / class (candidate t = flagged batch t / nc, flagged class t % nc)
@@ -1053,9 +1045,7 @@ __device__ __forceinline__ void tc_encode_body(const TcParams& p, const unsigned
           }
         }
         n_full += full ? 1u : 0u; n_cert += (!full && ncand == 1) ? 1u : 0u; n_resc += (!full && ncand > 1) ? 1u : 0u;
-#ifndef RVQ_NO_WIDE_COUNTERS
         if (!full && ncand > 4) { n_wide += 1u; n_widec += uint32_t(ncand); }
-#endif
         // upper bound of the next residual's |r|^2 (only the margin and the validity test use it):
         // the winner's approximate score is <= m + delta and off by <= delta/2
         if (full) { const float g2 = xnorm + mt_cmax; xx = g2 * g2; }
@@ -1113,10 +1103,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_encode_kernel(const TcParams
   PackView pv(p.pack, p.K, 128);
   const unsigned lo = __ballot_sync(0xffffffffu, lane < p.n_q && __ldg(&pv.meta(p.stage0 + lane)->percode) != 0);
   const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < p.n_q && __ldg(&pv.meta(p.stage0 + (lane + 32 < p.n_q ? lane + 32 : 0))->percode) != 0);
-  unsigned long long pcmask = (static_cast<unsigned long long>(hi) << 32) | lo;
-#ifdef RVQ_NO_PERCODE      // A/B builds: the per-code branch switched off
-  pcmask = 0ull;
-#endif
+  const unsigned long long pcmask = (static_cast<unsigned long long>(hi) << 32) | lo;
   // (the straight-through arithmetic of core_vq.py:309 is a compile-time property of the body too: as a run-time switch
   // inside the residual update it cost the training call 3 %)
   if (TRAIN && p.ste) {
