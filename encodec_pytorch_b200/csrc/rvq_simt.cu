@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
   unsigned long long* hashes = (unsigned long long*)(sh + Kp);   // K: 64-bit hash of every row (duplicate detection)
   unsigned long long* tab_h = hashes + K;                        // 2 Kp: open-addressing table of the hashes ...
   int* tab_i = (int*)(tab_h + 2 * Kp);                           // 2 Kp: ... and the lowest row index that carries each
-  unsigned char* outl = tc ? (unsigned char*)(tab_i + 2 * Kp) : (unsigned char*)(sh + Kp);   // K
+  float* e2s = (float*)(tab_i + 2 * Kp);                         // K: |(-2c) - fp16(-2c)|^2 of every row
+  unsigned char* outl = tc ? (unsigned char*)(e2s + K) : (unsigned char*)(sh + Kp);   // K
 
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
     float nv = __int_as_float(0x7f800000);
@@ -72,15 +73,18 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       // element (k, d) read from the transposed copy: consecutive threads touch consecutive addresses; the sum runs over d
       // in the same order as before
       const float* col = tT + k;
-      float acc = 0.f, amax = 0.f;
+      float acc = 0.f, amax = 0.f, e2 = 0.f;
       unsigned h1 = 0x811c9dc5u, h2 = 0x9747b28cu;      // two 32-bit multiplicative hashes of the row's bit patterns
+      #pragma unroll 8
       for (int d = 0; d < D; ++d) {
         float v = col[size_t(d) * K]; acc = fmaf(v, v, acc); amax = fmaxf(amax, fabsf(v));
         const unsigned bits = v == 0.f ? 0u : __float_as_uint(v);                   // (-0 and +0 are the same row element)
         h1 = h1 * 31u + bits;
         h2 = (h2 ^ bits) * 0x9e3779b1u;
+        // exact rounding residue of this code's fp16 operand row (-2c): |b - fp16(b)|^2
+        const float bb = -2.f * v; const float e = bb - __half2float(__float2half_rn(bb)); e2 = fmaf(e, e, e2);
       }
-      if (tc) hashes[k] = ((static_cast<unsigned long long>(h1) << 32) | h2) | 1ull;      // (0 marks an empty table slot)
+      if (tc) { hashes[k] = ((static_cast<unsigned long long>(h1) << 32) | h2) | 1ull; e2s[k] = e2; }      // (hash 0 marks an empty table slot)
       cn[k] = acc;
       nv = sqrtf(acc);
       // range flags for the fp16 image: B holds -2c, the augmented column holds |c|^2
@@ -164,10 +168,7 @@ __global__ void __launch_bounds__(1024) pack_meta_kernel(unsigned char* pack, in
       else if (alias) ++lnalias;
       else {
         lcref = fmaxf(lcref, nv);
-        // exact rounding residue of this code's fp16 operand row (-2c): |b - fp16(b)|^2
-        const float* col = tT + k;
-        float e2 = 0.f;
-        for (int d = 0; d < D; ++d) { const float b = -2.f * col[size_t(d) * K]; const float e = b - __half2float(__float2half_rn(b)); e2 = fmaf(e, e, e2); }
+        const float e2 = e2s[k];      // rounding residue of the fp16 operand row, from the first pass
         ldb2 = fmaxf(ldb2, e2);
         // per-code coefficients (StageMeta): |S_k - s_k| <= a_k |r| + b_k |r - fp16(r)|; the image carries
         // g16_k >= a_k + 2^-11 b_k (rounded UP to fp16, so that S_k - g16_k R stays a lower bound of s_k)
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256) pack_image_kernel(unsigned char* pack, in
 
 int simt_pack(const float* const* embed_ptrs_host, int n_q, int K, int D, void* pack, cudaStream_t st) {
   int Kp = 1; while (Kp < K) Kp <<= 1;
-  size_t meta_smem = size_t(Kp) * 4 + size_t(K) + (tc_shape(K, D) ? size_t(K) * 8 + size_t(Kp) * 24 : 0);
+  size_t meta_smem = size_t(Kp) * 4 + size_t(K) + (tc_shape(K, D) ? size_t(K) * 12 + size_t(Kp) * 24 : 0);
   RVQ_REQUIRE(meta_smem <= 200 * 1024, "rvq_pack: codebook_size %d too large", K);
   RVQ_CUDA(cudaFuncSetAttribute(pack_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta_smem));
   RVQ_CUDA(cudaMemsetAsync(pack, 0, kHeaderBytes, st));
