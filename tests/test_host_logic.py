@@ -35,6 +35,25 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib.rvq_last_error(), bytes)
 
 
+def test_pack_bound_mode_switch():
+    """rvq_pack_bound_mode is host state only: it hands back the previous mode, clamps garbage to the default, and the
+    context manager restores what it found."""
+    from encodec_pytorch_b200 import _lib as L, _ops as ops
+    lib = L.load()
+    prev = lib.rvq_pack_bound_mode(0)
+    try:
+        assert lib.rvq_pack_bound_mode(1) == 0 and lib.rvq_pack_bound_mode(2) == 1
+        assert lib.rvq_pack_bound_mode(7) == 2 and lib.rvq_pack_bound_mode(-3) == 0      # out of range -> default
+        assert lib.rvq_pack_bound_mode(0) == 0
+        with ops.pack_bound_mode(2):
+            with ops.pack_bound_mode(1):
+                assert lib.rvq_pack_bound_mode(1) == 1
+            assert lib.rvq_pack_bound_mode(2) == 2
+        assert lib.rvq_pack_bound_mode(0) == 0
+    finally:
+        lib.rvq_pack_bound_mode(prev)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
 def test_compute_entry_points_refuse_without_device():
     from encodec_pytorch_b200 import _lib as L
